@@ -1,0 +1,441 @@
+#!/usr/bin/env python3
+"""bench.py - particle events/s of neutral's particle-history hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--deck csp] [--particles P]
+
+One "step" = one complete run of the deck named in ``config.workload`` (default csp: 4000 x
+4000 mesh, 1e6 particles per GPU, 10 timesteps of solve_transport_2d) from the freshly
+injected bank. Prints ONE JSON line (rank 0):
+
+* ``value``     whole-job events/s ( facets + collisions + census over all ranks and the K
+                timed steps / device time, max over ranks ), inputs resident in HBM;
+* ``e2e``       the same metric with HOST buffers: every step uploads the deck (mesh,
+                cross sections, bank) from pinned host memory, runs the timesteps through
+                solve_transport_2d, and reads tally, bank and counters back;
+* ``roofline``  the history kernel against the measured HBM peak, algorithmic bytes per
+                event from SURVEY.md 8d (facet 200 B, collision 176 B, census 192 B, fatal
+                collision +16 B);
+* ``cpu_baseline`` the unmodified reference omp3 build (oracle/_ref) on this box's host
+                cores, on a bounded sample of the same deck (N=1 only).
+
+``--impl reference`` times the reference's own CPU implementation instead (rank 0 only).
+N > 1 (torchrun): weak scaling - every rank transports ``deck.nparticles`` particles of an
+N-times larger global bank (global RNG keys), and the per-timestep tally deltas are
+all-reduced with NCCL.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "particle_events_per_sec"
+UNIT = "events/s"
+# algorithmic bytes per event of the event-based model
+B_FACET, B_COLLISION, B_CENSUS, B_DEATH_EXTRA = 200.0, 176.0, 192.0, 16.0
+FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--deck", default="csp")
+    ap.add_argument("--particles", type=int, default=0, help="override particles per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------ clocks --
+
+class ClockSampler:
+    """Samples nvidia-smi during the timed region (B200_PROFILING.md clocks line)."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "200", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------- reference (CPU) arm --
+
+def reference_rate(deck_name: str, target_seconds: float, steps: int = 1, warmup: int = 0):
+    """Times the unmodified reference omp3 build (oracle/_ref, else the oracle port) on this
+    host, all cores, on a bounded sample of the deck. Returns a dict for the JSON line."""
+    from neutral_b200.decks import build_problem, load_deck
+    from oracle.oracle import OraclePort, ReferenceOmp3
+
+    cores = len(os.sched_getaffinity(0))
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    kind = "reference" if ReferenceOmp3.available() else "port"
+    eng = ReferenceOmp3() if kind == "reference" else OraclePort()
+    deck = load_deck(deck_name)
+
+    def run_once(nparticles):
+        prob = build_problem(deck, nparticles=nparticles)
+        d = prob.deck
+        tally = np.zeros(d.nx * d.ny)
+        if kind == "reference":
+            bank = eng.inject(prob)
+        else:
+            bank = eng.inject(prob)
+        events, seconds = 0, 0.0
+        for tt in range(1, d.iterations + 1):
+            if kind == "reference":
+                alive0 = int(np.count_nonzero(bank["dead"] == 0))
+                t0 = time.perf_counter()
+                f, c = eng.step(prob, bank, tt, tally)
+                seconds += time.perf_counter() - t0
+                alive1 = int(np.count_nonzero(bank["dead"] == 0))
+                events += f + c + alive1  # census = processed particles that did not die
+                del alive0
+            else:
+                t0 = time.perf_counter()
+                f, c, p = eng.step(prob, bank, tt, tally)
+                seconds += time.perf_counter() - t0
+                events += f + c + int(np.count_nonzero(bank.dead == 0))
+        return events, seconds
+
+    # calibrate on a small sample, then size the real one for ~target_seconds per step
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)  # the reference prints "Particles N" every timestep
+    try:
+        n0 = min(deck.nparticles, 2000 * cores)
+        ev0, s0 = run_once(n0)
+        rate0 = ev0 / max(s0, 1e-9)
+        per_particle = ev0 / n0
+        n = int(min(deck.nparticles, max(n0, rate0 * target_seconds / per_particle)))
+        times, events = [], 0
+        for i in range(warmup + steps):
+            ev, s = run_once(n)
+            if i >= warmup:
+                times.append(s)
+                events += ev
+    finally:
+        os.dup2(saved, 1)
+        os.close(devnull)
+    total = sum(times)
+    return {"value": events / total, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{deck.name}: {n} of {deck.nparticles} particles, {deck.iterations} "
+                      f"timesteps, {deck.nx}x{deck.ny} mesh, {steps} run(s) of "
+                      f"{total / max(steps, 1):.1f} s, OMP threads={cores}",
+            "ms_per_step": 1e3 * total / max(steps, 1), "events_per_step": events / max(steps, 1)}
+
+
+def run_reference_arm(args, rank: int):
+    if rank != 0:
+        return
+    budget = 150.0 / max(args.steps + args.warmup, 1)
+    res = reference_rate(args.deck, target_seconds=min(10.0, budget), steps=args.steps,
+                         warmup=args.warmup)
+    from neutral_b200.decks import load_deck
+    deck = load_deck(args.deck)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{deck.name}.params (bounded sample, see cpu_baseline.sample)",
+                   "mesh": [deck.nx, deck.ny], "timesteps_per_step": deck.iterations},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------- b200 (GPU) arm --
+
+def algorithmic_bytes(results):
+    return sum(r.facets * B_FACET + r.collisions * B_COLLISION + r.census * B_CENSUS +
+               r.deaths * B_DEATH_EXTRA for r in results)
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except (OSError, KeyError, ValueError):
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_per_launch(deck_name):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get(deck_name, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        return None
+
+
+def run_b200_arm(args, rank: int, local_rank: int, world: int):
+    import torch
+    import torch.distributed as dist
+
+    from neutral_b200.bank import HostBank
+    from neutral_b200.decks import build_problem, load_deck
+    from neutral_b200.host import Simulation, _check, _soa_p, load_library
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = load_library(build=False)
+    lib.initialise_devices.restype = None
+    lib.nb200_set_option(b"print", 0)
+
+    deck = load_deck(args.deck)
+    per_gpu = args.particles or deck.nparticles
+    prob = build_problem(deck, nparticles=per_gpu * world)  # weak scaling: global bank grows
+    d = prob.deck
+    ncells = d.nx * d.ny
+
+    sim = Simulation(prob, rank=rank, nranks=world, per_particle_counters=False)
+    sim.inject()
+    start_bank = sim.bank_to_host()  # host copy of the freshly injected shard
+    # resident snapshot the timed steps restart from
+    snap = _soa_p()
+    st = start_bank.as_struct()
+    _check(lib.nb200_bank_create(C.byref(st), sim.count, sim.pid0, C.byref(snap)), "snapshot")
+
+    delta = torch.zeros(ncells, dtype=torch.float64, device="cuda") if world > 1 else None
+
+    def one_step():
+        """One deck run from the injected state; returns the list of StepResults."""
+        _check(lib.nb200_bank_copy(sim.bank, snap), "bank_copy")
+        sim.tally.zero()
+        out = []
+        for tt in range(1, d.iterations + 1):
+            if world > 1:
+                delta.zero_()
+                out.append(sim.step(tt, tally_ptr=delta.data_ptr()))
+                dist.all_reduce(delta)
+                _check(lib.nb200_accumulate(sim.tally.ptr, delta.data_ptr(), ncells), "acc")
+            else:
+                out.append(sim.step(tt))
+        return out
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.nb200_kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fence()
+    ev0.record()
+    timed = []
+    for _ in range(args.steps):
+        timed += one_step()
+    ev1.record()
+    fence()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = lib.nb200_kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    events = sum(r.events for r in timed)
+    kernel_ns = sum(r.kernel_ns for r in timed)
+    hist_launches = len(timed)
+    alg_bytes = algorithmic_bytes(timed)
+    tally_sum = float(torch.from_numpy(sim.tally_to_host()).sum()) if rank == 0 else 0.0
+
+    # ---- e2e: host buffers in, host buffers out, every step ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        h_density, h_ex, h_ey = pin(prob.density.ravel()), pin(prob.edgex), pin(prob.edgey)
+        h_cs = [pin(a) for pair in (prob.cs_scatter, prob.cs_absorb) for a in pair]
+        h_bank = {k: pin(v) for k, v in start_bank.arrays.items()}
+        h_bank_struct = HostBank({k: v.numpy() for k, v in h_bank.items()}).as_struct()
+        out_tally = torch.empty(ncells, dtype=torch.float64).pin_memory()
+        out_bank = HostBank({k: torch.empty_like(v).pin_memory().numpy()
+                             for k, v in h_bank.items()})
+        out_struct = out_bank.as_struct()
+        dev_inputs = [(sim.density, h_density), (sim.edgex, h_ex), (sim.edgey, h_ey)] + \
+            list(zip(sim._cs_arrays, h_cs))
+        h2d = sum(t.numel() * t.element_size() for _, t in dev_inputs) + \
+            sum(t.numel() * t.element_size() for t in h_bank.values())
+        d2h = out_tally.numel() * 8 + sum(t.numel() * t.element_size() for t in h_bank.values())
+
+        def e2e_step():
+            for dev, host in dev_inputs:
+                _check(lib.nb200_memcpy_h2d(dev.ptr, host.data_ptr(),
+                                            host.numel() * host.element_size()), "h2d")
+            _check(lib.nb200_bank_upload(sim.bank, C.byref(h_bank_struct)), "bank_upload")
+            sim.tally.zero()
+            out = []
+            for tt in range(1, d.iterations + 1):
+                if world > 1:
+                    delta.zero_()
+                    out.append(sim.step(tt, tally_ptr=delta.data_ptr()))
+                    dist.all_reduce(delta)
+                    _check(lib.nb200_accumulate(sim.tally.ptr, delta.data_ptr(), ncells), "acc")
+                else:
+                    out.append(sim.step(tt))
+            _check(lib.nb200_memcpy_d2h(out_tally.data_ptr(), sim.tally.ptr, ncells * 8), "d2h")
+            _check(lib.nb200_bank_download(sim.bank, C.byref(out_struct)), "bank_download")
+            return out
+
+        for _ in range(min(args.warmup, 2)):
+            e2e_step()
+        fence()
+        t0 = time.perf_counter()
+        e2e_res = []
+        for _ in range(args.steps):
+            e2e_res += e2e_step()
+        fence()
+        e2e_s = time.perf_counter() - t0
+        e2e = {"events": sum(r.events for r in e2e_res), "seconds": e2e_s, "h2d": h2d,
+               "d2h": d2h, "tally_sum": float(out_tally.sum())}
+
+    # ---- reduce over ranks -------------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([elapsed_ms, e2e["seconds"] if e2e else 0.0], device="cuda",
+                         dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c = torch.tensor([events, e2e["events"] if e2e else 0, launches, kernel_ns, alg_bytes],
+                         device="cuda", dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        elapsed_ms, e2e_seconds = float(t[0]), float(t[1])
+        events_all, e2e_events_all, launches_all = float(c[0]), float(c[1]), int(c[2])
+    else:
+        e2e_seconds = e2e["seconds"] if e2e else 0.0
+        events_all, e2e_events_all, launches_all = float(events), \
+            float(e2e["events"]) if e2e else 0.0, int(launches)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_hbm_peak()
+    # dominant kernel = the history kernel; per-launch figures of THIS rank (rank 0)
+    ach_gbs = (alg_bytes / max(kernel_ns, 1))  # bytes per ns == GB/s
+    roofline = {
+        "bound": "hbm", "kernel": "k_history_direct", "achieved": ach_gbs, "peak": peak,
+        "unit": "GB/s", "frac": ach_gbs / peak, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": alg_bytes / max(hist_launches, 1),
+        "avg_launch_ms": kernel_ns / max(hist_launches, 1) / 1e6,
+        "launches_timed": hist_launches,
+        "kernel_share_of_step": (kernel_ns / 1e6) / max(elapsed_ms, 1e-9),
+        "traffic": ncu_traffic_per_launch(deck.name),
+    }
+    line = {
+        "metric": METRIC, "value": events_all / (elapsed_ms / 1e3), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{deck.name}.params: {d.nx}x{d.ny} mesh, {per_gpu} particles "
+                               f"per GPU ({d.nparticles} global), {d.iterations} timesteps "
+                               "per step, fresh bank each step",
+                   "l2_policy": "inputs larger than L2 (density + tally = "
+                                f"{2 * ncells * 8 / 2**20:.0f} MiB, random access)",
+                   "parallelism": f"particle-sharded x{world}, NCCL all-reduce of the tally "
+                                  "delta per timestep" if world > 1 else "single GPU",
+                   "events_per_step": events_all / args.steps,
+                   "tally_sum": tally_sum},
+        "roofline": roofline,
+        "clocks": clocks,
+        "gpu_launches": launches_all,
+    }
+    if e2e:
+        line["e2e"] = {"value": e2e_events_all / e2e_seconds, "unit": UNIT,
+                       "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                       "ms_per_step": 1e3 * e2e_seconds / args.steps,
+                       "tally_sum": e2e["tally_sum"]}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            res = reference_rate(args.deck, target_seconds=15.0)
+            line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as exc:  # the baseline is a reported number, never a gate
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                                    "sample": f"unavailable: {exc}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        sys.exit("bench.py --gpus N>1 must be launched with torch.distributed.run "
+                 "(one process per GPU)")
+    run_b200_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

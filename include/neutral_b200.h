@@ -1,0 +1,217 @@
+/*
+ * neutral_b200.h - C ABI of the B200 (sm_100a) kernel set for UoB-HPC/neutral.
+ *
+ * libneutral_b200.so is a drop-in `KERNELS=b200` kernel set: it exports the three functions
+ * of the reference plugin boundary (neutral_interface.h:11-36) with the reference's names,
+ * argument order and meaning, plus the per-kernel-set allocation layer the reference's host
+ * driver expects from its parent `arch` project (call sites neutral_data.c:54-62,97-105,
+ * 146-147,168-169; main.c:63). The reference's unmodified main.c + neutral_data.c link
+ * against it when compiled with -DSoA (the layout every GPU kernel set of the reference
+ * uses, Makefile:60-71). Everything else in this header (nb200_*) is an extension for
+ * callers that are not the C driver: FFI hosts, the parity tests, the bench harness.
+ *
+ * Plain C: pointers and sizes only. The types below are layout-compatible with the
+ * reference's `Particle` (-DSoA, neutral_data.h:48-61) and `CrossSection`
+ * (neutral_data.h:38-43); they carry their own names so this header can be included next
+ * to, or without, the reference's neutral_data.h.
+ *
+ * Memory spaces. In the device-resident flavour (section 1) every array argument is DEVICE
+ * memory on the current GPU, obtained from the allocation layer (section 2) or from any
+ * other CUDA allocator (e.g. a torch tensor's data_ptr); scalars passed by pointer
+ * (nlocal_particles, facet_events, collision_events) and the CrossSection structs
+ * themselves are HOST memory. Section 3 has the host-buffer flavour.
+ *
+ * Errors. Like the reference (arch TERMINATE, used e.g. omp3/neutral.c:572) the three
+ * boundary functions print a message and exit(EXIT_FAILURE) on a fatal error - including a
+ * missing GPU: there is no CPU fallback. nb200_* functions return 0 on success and a
+ * negative code on failure, with nb200_last_error() describing it.
+ */
+#ifndef NEUTRAL_B200_H
+#define NEUTRAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB200_ABI_VERSION 1
+
+/* == reference `Particle` under -DSoA (neutral_data.h:48-61) */
+typedef struct {
+  double* x;
+  double* y;
+  double* omega_x;
+  double* omega_y;
+  double* energy;
+  double* weight;
+  double* dt_to_census;
+  double* mfp_to_collision;
+  int* cellx;
+  int* celly;
+  int* dead;
+} nb200_particle_soa;
+
+/* == reference AoS `Particle` (neutral_data.h:66-79), 80 bytes */
+typedef struct {
+  double x, y, omega_x, omega_y, energy, weight, dt_to_census, mfp_to_collision;
+  int cellx, celly, dead;
+} nb200_particle_aos;
+
+/* == reference `CrossSection` (neutral_data.h:38-43) */
+typedef struct {
+  double* keys;
+  double* values;
+  int nentries;
+} nb200_cross_section;
+
+/* ------------------------------------------------------------------------------------
+ * 1. The plugin boundary, device-resident flavour (replaces omp3/neutral.c:19-40,
+ *    :520-557, :560-630 behind neutral_interface.h:11-36).
+ * ---------------------------------------------------------------------------------- */
+
+/* One timestep of the whole local bank. Replaces solve_transport_2d
+ * (neutral_interface.h:11-20 / omp3/neutral.c:19-40). `particles` is the handle returned by
+ * inject_particles (or nb200_bank_create); *facet_events and *collision_events are ADDED
+ * to, as omp3 does (omp3/neutral.c:202-203); prints "Particles  <n>" (omp3/neutral.c:205).
+ * reduce_array0..2, when non-null, are uint64[bank size] device arrays that receive the
+ * cumulative per-particle facet / collision / census counts in injection order.
+ * pad must be 0 and x_off = y_off = 0 (the only configuration main.c:34,101-110 produces). */
+void solve_transport_2d(
+    const int nx, const int ny, const int global_nx, const int global_ny,
+    const uint64_t master_key, const int pad, const int x_off, const int y_off,
+    const double dt, const int ntotal_particles, int* nlocal_particles,
+    const int* neighbours, nb200_particle_soa* particles, const double* density,
+    const double* edgex, const double* edgey, const double* edgedx,
+    const double* edgedy, nb200_cross_section* cs_scatter_table,
+    nb200_cross_section* cs_absorb_table, double* energy_deposition_tally,
+    uint64_t* reduce_array0, uint64_t* reduce_array1, uint64_t* reduce_array2,
+    uint64_t* facet_events, uint64_t* collision_events);
+
+/* Creates and fills the bank. Replaces inject_particles (neutral_interface.h:23-31 /
+ * omp3/neutral.c:560-630): positions, cells and directions come from the same
+ * Threefry-2x64 streams and the same libm cos/sin as the reference, computed on the host
+ * and uploaded. Returns the bytes of device memory allocated; *particles receives an
+ * opaque handle whose first 11 members alias a plain SoA view (see nb200_bank_export). */
+size_t inject_particles(const int nparticles, const int global_nx, const int local_nx,
+                        const int local_ny, const int pad,
+                        const double local_particle_left_off,
+                        const double local_particle_bottom_off,
+                        const double local_particle_width,
+                        const double local_particle_height, const int x_off,
+                        const int y_off, const double dt, const double* edgex,
+                        const double* edgey, const double initial_energy,
+                        nb200_particle_soa** particles);
+
+/* Sums the tally on the device and compares it with problems/neutral.tests at 1e-3.
+ * Replaces validate (neutral_interface.h:35-36 / omp3/neutral.c:520-557); same printed lines. */
+void validate(const int nx, const int ny, const char* params_filename, const int rank,
+              double* energy_tally);
+
+/* ------------------------------------------------------------------------------------
+ * 2. Allocation layer of the kernel set (arch `shared.h`; restated in archlite/shared.h).
+ *    Kernel-set memory = device memory on the current GPU, zero-filled.
+ * ---------------------------------------------------------------------------------- */
+size_t allocate_data(double** buf, size_t len);
+size_t allocate_float_data(float** buf, size_t len);
+size_t allocate_int_data(int** buf, size_t len);
+size_t allocate_uint64_data(uint64_t** buf, size_t len);
+void allocate_host_data(double** buf, size_t len);       /* pinned host memory */
+void allocate_host_float_data(float** buf, size_t len);  /* pinned host memory */
+void deallocate_data(double* buf);
+void deallocate_host_data(double* buf);
+/* send != 0: host -> device, send == 0 (RECV): device -> host; len doubles. */
+void copy_buffer(const size_t len, double** src, double** dst, int send);
+/* Uploads len doubles to a fresh device buffer (*dst) and frees the host buffer. */
+void move_host_buffer_to_device(const size_t len, double** src, double** dst);
+/* Binds the process to GPU `rank % device count` (main.c:63). */
+void initialise_devices(int rank);
+
+/* ------------------------------------------------------------------------------------
+ * 3. Host-buffer flavour: the omp3 signature on HOST arrays (AoS bank, as
+ *    omp3/neutral.c:19-40 takes it). Every call uploads what it reads, runs the same
+ *    kernels, and downloads what it writes (bank, tally). For FFI hosts and parity tests.
+ * ---------------------------------------------------------------------------------- */
+void nb200_solve_transport_2d_host(
+    const int nx, const int ny, const int global_nx, const int global_ny,
+    const uint64_t master_key, const int pad, const int x_off, const int y_off,
+    const double dt, const int ntotal_particles, int* nlocal_particles,
+    const int* neighbours, nb200_particle_aos* particles, const double* density,
+    const double* edgex, const double* edgey, const double* edgedx,
+    const double* edgedy, nb200_cross_section* cs_scatter_table,
+    nb200_cross_section* cs_absorb_table, double* energy_deposition_tally,
+    uint64_t* reduce_array0, uint64_t* reduce_array1, uint64_t* reduce_array2,
+    uint64_t* facet_events, uint64_t* collision_events);
+
+/* ------------------------------------------------------------------------------------
+ * 4. Extensions
+ * ---------------------------------------------------------------------------------- */
+int nb200_abi_version(void);
+const char* nb200_last_error(void);
+/* Number of CUDA devices visible (0 = none: every compute entry point fails loudly). */
+int nb200_device_count(void);
+/* CUDA stream (cudaStream_t) all work is enqueued on; default 0 = the legacy default stream. */
+int nb200_set_stream(void* cuda_stream);
+
+/* Particle sharding across GPUs: the next inject_particles builds only global particles
+ * [first, first+count) of the nparticles it is asked for (RNG keys stay global), the same
+ * contiguous split omp3 uses for its threads (omp3/neutral.c:64-74). count < 0 clears. */
+int nb200_set_shard(int first, int count);
+
+/* Bank from host SoA arrays holding global particles [pid_first, pid_first+count). */
+int nb200_bank_create(const nb200_particle_soa* host, int count, int pid_first,
+                      nb200_particle_soa** particles);
+/* Copies the bank to host SoA arrays in injection order (count = bank size). */
+int nb200_bank_download(nb200_particle_soa* particles, nb200_particle_soa* host);
+/* Overwrites the bank from host SoA arrays (asynchronous on the library's stream; pinned
+ * host memory makes the copies truly asynchronous). */
+int nb200_bank_upload(nb200_particle_soa* particles, const nb200_particle_soa* host);
+/* Refreshes the plain device SoA view behind the handle's 11 pointers. */
+int nb200_bank_export(nb200_particle_soa* particles);
+/* Overwrites the bank's state from another bank of the same size (device to device). */
+int nb200_bank_copy(nb200_particle_soa* dst, nb200_particle_soa* src);
+int nb200_bank_size(nb200_particle_soa* particles);
+int nb200_bank_free(nb200_particle_soa* particles);
+
+/* Raw device/host copies for hosts without a CUDA binding of their own. */
+int nb200_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes);
+int nb200_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes);
+int nb200_memset_d(void* dst_device, int value, size_t bytes);
+int nb200_synchronize(void);
+
+/* dst[i] += src[i] on the device: combines per-step tally deltas of a particle-sharded run
+ * (after the all-reduce of the deltas). */
+int nb200_accumulate(double* dst_device, const double* src_device, size_t n);
+
+/* Options: "print" (1: print the reference's "Particles" line), "pipeline"
+ * (0: direct one-thread-per-history kernel, 1: phased pipeline - default).
+ * Returns the previous value, or a negative code for an unknown name. */
+int nb200_set_option(const char* name, int value);
+
+/* Statistics of the most recent solve_transport_2d: out[0..4] = facets, collisions,
+ * particles processed, census events, deaths; out[5] = kernels launched by that call;
+ * out[6] = nanoseconds the step's history kernels took on the stream (CUDA events). */
+int nb200_last_step_stats(uint64_t out[8]);
+/* Kernels launched by this library since load (monotonic). */
+uint64_t nb200_kernel_launches(void);
+
+/* Known-answer hooks on the bit-exact building blocks (device and host builds of the same
+ * source). raw/unit/neglog hold 2n entries: Threefry-2x64-20(ctr={counter,0},
+ * key={pkey0+i, master_key}), the (0,1] doubles, and -log of them. */
+int nb200_selftest_rng_log(uint64_t pkey0, uint64_t master_key, uint64_t counter, int n,
+                           uint64_t* raw_host, double* unit_host, double* neglog_host);
+int nb200_selftest_log(const double* x_host, double* y_host, int n);
+int nb200_selftest_cs(const double* keys_host, const double* values_host, int nentries,
+                      const double* energies_host, int n, int* index_host,
+                      double* value_host);
+/* Host builds (no GPU needed). */
+void nb200_host_threefry2x64_20(uint64_t c0, uint64_t c1, uint64_t k0, uint64_t k1,
+                                uint64_t out[2]);
+double nb200_host_log(double x);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* NEUTRAL_B200_H */

@@ -1,0 +1,875 @@
+// capi.cu - the C ABI of libneutral_b200.so (declared in include/neutral_b200.h).
+//
+// Host-side glue only: argument checking, device memory, stream ordering, counters. The
+// arithmetic of the hot path lives in transport.cu. There is deliberately no CPU fallback:
+// every compute entry point fails loudly when no CUDA device is usable.
+#include "../../include/neutral_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "transport.cuh"
+
+namespace {
+
+using namespace nb;
+
+const LogTable kHostLogTable = {
+#include "glibc_log_table.inc"
+};
+
+constexpr uint64_t kBankMagic = 0x6e62323030424e4bull;  // "nb200BNK"
+
+struct Bank {
+  BankView cur{};
+  int n = 0;
+  uint64_t pid0 = 0;
+  SoaView exported{};  // lazily allocated plain SoA view (11 arrays)
+  bool has_export = false;
+};
+
+// What inject_particles / nb200_bank_create hand out as `Particle*`: the reference's SoA
+// struct first (so -DSoA code can read the 11 pointers), our bookkeeping after it.
+struct BankHandle {
+  nb200_particle_soa view;
+  uint64_t magic;
+  Bank* impl;
+};
+
+struct Context {
+  bool ready = false;
+  int device = 0;
+  cudaStream_t stream = 0;
+  LogTable* d_logt = nullptr;
+  unsigned long long* d_totals = nullptr;
+  unsigned long long* h_totals = nullptr;  // pinned
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // bracket the history kernels of a step
+  uint64_t launches = 0;
+  uint64_t last_stats[8] = {0};
+  int opt_print = 1;
+  int opt_pipeline = 1;
+  int shard_first = 0;
+  int shard_count = -1;
+  // cross-section grids seen last (same-grid detection is cached per table pair)
+  const double* cs_s_keys = nullptr;
+  const double* cs_a_keys = nullptr;
+  int cs_n = 0;
+  int cs_same = 0;
+  std::string last_error;
+};
+
+Context g;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g.last_error = buf;
+}
+
+[[noreturn]] void terminate(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  fprintf(stderr, "neutral_b200: fatal: %s\n", buf);
+  fflush(stderr);
+  exit(EXIT_FAILURE);
+}
+
+#define CU_FATAL(call)                                                              \
+  do {                                                                              \
+    cudaError_t err__ = (call);                                                     \
+    if (err__ != cudaSuccess)                                                       \
+      terminate("%s failed: %s [%s:%d]", #call, cudaGetErrorString(err__), __FILE__, \
+                __LINE__);                                                          \
+  } while (0)
+
+#define CU_TRY(call)                                                                \
+  do {                                                                              \
+    cudaError_t err__ = (call);                                                     \
+    if (err__ != cudaSuccess) {                                                     \
+      set_error("%s failed: %s [%s:%d]", #call, cudaGetErrorString(err__), __FILE__, \
+                __LINE__);                                                          \
+      return -2;                                                                    \
+    }                                                                               \
+  } while (0)
+
+// Returns 0 when a device is usable and the context is initialised.
+int ensure_ready() {
+  if (g.ready) return 0;
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count <= 0) {
+    set_error("no CUDA device available (%s): the b200 kernel set has no CPU fallback",
+              err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0");
+    (void)cudaGetLastError();
+    return -1;
+  }
+  CU_TRY(cudaGetDevice(&g.device));
+  CU_TRY(cudaMalloc(&g.d_logt, sizeof(LogTable)));
+  CU_TRY(cudaMemcpy(g.d_logt, &kHostLogTable, sizeof(LogTable), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMalloc(&g.d_totals, sizeof(unsigned long long) * kTotCount));
+  CU_TRY(cudaMallocHost(&g.h_totals, sizeof(unsigned long long) * kTotCount));
+  CU_TRY(cudaEventCreate(&g.ev_begin));
+  CU_TRY(cudaEventCreate(&g.ev_end));
+  g.ready = true;
+  return 0;
+}
+
+void require_ready() {
+  if (ensure_ready() != 0) terminate("%s", g.last_error.c_str());
+}
+
+template <typename T>
+size_t device_zalloc(T** buf, size_t len) {
+  require_ready();
+  const size_t bytes = sizeof(T) * (len ? len : 1);
+  CU_FATAL(cudaMalloc((void**)buf, bytes));
+  CU_FATAL(cudaMemsetAsync(*buf, 0, bytes, g.stream));
+  return sizeof(T) * len;
+}
+
+size_t bank_alloc(BankView& b, int n) {
+  size_t bytes = 0;
+  bytes += device_zalloc(&b.pos, (size_t)n);
+  bytes += device_zalloc(&b.dir, (size_t)n);
+  bytes += device_zalloc(&b.ew, (size_t)n);
+  bytes += device_zalloc(&b.tm, (size_t)n);
+  bytes += device_zalloc(&b.meta, (size_t)n);
+  return bytes;
+}
+
+void bank_release(BankView& b) {
+  cudaFree(b.pos);
+  cudaFree(b.dir);
+  cudaFree(b.ew);
+  cudaFree(b.tm);
+  cudaFree(b.meta);
+  b = BankView{};
+}
+
+size_t soa_alloc(SoaView& s, int n) {
+  size_t bytes = 0;
+  double** d[] = {&s.x, &s.y, &s.omega_x, &s.omega_y, &s.energy, &s.weight,
+                  &s.dt_to_census, &s.mfp_to_collision};
+  for (double** p : d) bytes += device_zalloc(p, (size_t)n);
+  int** i[] = {&s.cellx, &s.celly, &s.dead};
+  for (int** p : i) bytes += device_zalloc(p, (size_t)n);
+  return bytes;
+}
+
+void soa_release(SoaView& s) {
+  void* p[] = {s.x, s.y, s.omega_x, s.omega_y, s.energy, s.weight, s.dt_to_census,
+               s.mfp_to_collision, s.cellx, s.celly, s.dead};
+  for (void* q : p) cudaFree(q);
+  s = SoaView{};
+}
+
+SoaView as_soa_view(const nb200_particle_soa& p) {
+  SoaView s;
+  s.x = p.x; s.y = p.y; s.omega_x = p.omega_x; s.omega_y = p.omega_y;
+  s.energy = p.energy; s.weight = p.weight; s.dt_to_census = p.dt_to_census;
+  s.mfp_to_collision = p.mfp_to_collision;
+  s.cellx = p.cellx; s.celly = p.celly; s.dead = p.dead;
+  return s;
+}
+
+nb200_particle_soa as_public(const SoaView& s) {
+  nb200_particle_soa p;
+  p.x = s.x; p.y = s.y; p.omega_x = s.omega_x; p.omega_y = s.omega_y;
+  p.energy = s.energy; p.weight = s.weight; p.dt_to_census = s.dt_to_census;
+  p.mfp_to_collision = s.mfp_to_collision;
+  p.cellx = s.cellx; p.celly = s.celly; p.dead = s.dead;
+  return p;
+}
+
+BankHandle* new_handle(int n, uint64_t pid0, size_t* bytes) {
+  BankHandle* h = (BankHandle*)calloc(1, sizeof(BankHandle));
+  h->impl = new Bank();
+  h->magic = kBankMagic;
+  h->impl->n = n;
+  h->impl->pid0 = pid0;
+  const size_t b = bank_alloc(h->impl->cur, n);
+  if (bytes) *bytes = b;
+  return h;
+}
+
+Bank* bank_of(nb200_particle_soa* particles) {
+  if (!particles) return nullptr;
+  BankHandle* h = reinterpret_cast<BankHandle*>(particles);
+  if (h->magic != kBankMagic || !h->impl) return nullptr;
+  return h->impl;
+}
+
+// Uploads a host SoA bank (count slots) into device bank b, tagging origins from 0.
+void upload_host_soa(const SoaView& host, int count, BankView& dst) {
+  SoaView staging{};
+  soa_alloc(staging, count);
+  const double* hd[] = {host.x, host.y, host.omega_x, host.omega_y, host.energy, host.weight,
+                        host.dt_to_census, host.mfp_to_collision};
+  double* dd[] = {staging.x, staging.y, staging.omega_x, staging.omega_y, staging.energy,
+                  staging.weight, staging.dt_to_census, staging.mfp_to_collision};
+  for (int k = 0; k < 8; ++k)
+    CU_FATAL(cudaMemcpyAsync(dd[k], hd[k], sizeof(double) * count, cudaMemcpyHostToDevice,
+                             g.stream));
+  const int* hi[] = {host.cellx, host.celly, host.dead};
+  int* di[] = {staging.cellx, staging.celly, staging.dead};
+  for (int k = 0; k < 3; ++k)
+    CU_FATAL(cudaMemcpyAsync(di[k], hi[k], sizeof(int) * count, cudaMemcpyHostToDevice,
+                             g.stream));
+  g.launches += launch_import_soa(dst, staging, count, 0, g.stream);
+  CU_FATAL(cudaStreamSynchronize(g.stream));
+  soa_release(staging);
+}
+
+int detect_same_grid(const double* s_keys, int s_n, const double* a_keys, int a_n) {
+  if (s_n != a_n) return 0;
+  if (s_keys == a_keys) return 1;
+  if (g.cs_s_keys == s_keys && g.cs_a_keys == a_keys && g.cs_n == s_n) return g.cs_same;
+  std::vector<double> hs(s_n), ha(a_n);
+  CU_FATAL(cudaMemcpyAsync(hs.data(), s_keys, sizeof(double) * s_n, cudaMemcpyDeviceToHost,
+                           g.stream));
+  CU_FATAL(cudaMemcpyAsync(ha.data(), a_keys, sizeof(double) * a_n, cudaMemcpyDeviceToHost,
+                           g.stream));
+  CU_FATAL(cudaStreamSynchronize(g.stream));
+  g.cs_s_keys = s_keys;
+  g.cs_a_keys = a_keys;
+  g.cs_n = s_n;
+  g.cs_same = memcmp(hs.data(), ha.data(), sizeof(double) * s_n) == 0;
+  return g.cs_same;
+}
+
+// The one timestep both flavours share. All pointers are device memory.
+void run_step(Bank* bank, int nx, int ny, uint64_t master_key, double dt, int ntotal,
+              const double* density, const double* edgex, const double* edgey,
+              const double* s_keys, const double* s_vals, int s_n, const double* a_keys,
+              const double* a_vals, int a_n, double* tally, uint64_t* r0, uint64_t* r1,
+              uint64_t* r2, uint64_t* facet_events, uint64_t* collision_events) {
+  const uint64_t launches0 = g.launches;
+  StepArgs a{};
+  a.nx = nx;
+  a.ny = ny;
+  a.n = bank->n;
+  a.master_key = master_key;
+  a.pid0 = bank->pid0;
+  a.dt = dt;
+  a.inv_ntotal = 1.0 / (double)ntotal;  // omp3/neutral.c:120
+  a.density = density;
+  a.edgex = edgex;
+  a.edgey = edgey;
+  a.s_keys = s_keys;
+  a.s_vals = s_vals;
+  a.s_n = s_n;
+  a.a_keys = a_keys;
+  a.a_vals = a_vals;
+  a.a_n = a_n;
+  a.same_keys = detect_same_grid(s_keys, s_n, a_keys, a_n);
+  a.tally = tally;
+  a.p_facets = (unsigned long long*)r0;
+  a.p_collisions = (unsigned long long*)r1;
+  a.p_census = (unsigned long long*)r2;
+  a.totals = g.d_totals;
+  a.bank = bank->cur;
+  a.logt = g.d_logt;
+
+  CU_FATAL(cudaMemsetAsync(g.d_totals, 0, sizeof(unsigned long long) * kTotCount, g.stream));
+  CU_FATAL(cudaEventRecord(g.ev_begin, g.stream));
+  g.launches += launch_history_direct(a, g.stream);
+  CU_FATAL(cudaGetLastError());
+  CU_FATAL(cudaEventRecord(g.ev_end, g.stream));
+  CU_FATAL(cudaMemcpyAsync(g.h_totals, g.d_totals, sizeof(unsigned long long) * kTotCount,
+                           cudaMemcpyDeviceToHost, g.stream));
+  CU_FATAL(cudaStreamSynchronize(g.stream));
+
+  for (int k = 0; k < kTotCount; ++k) g.last_stats[k] = g.h_totals[k];
+  g.last_stats[5] = g.launches - launches0;
+  float kernel_ms = 0.0f;
+  CU_FATAL(cudaEventElapsedTime(&kernel_ms, g.ev_begin, g.ev_end));
+  g.last_stats[6] = (uint64_t)((double)kernel_ms * 1.0e6);  // ns on the launching stream
+  *facet_events += g.h_totals[kTotFacets];          // omp3/neutral.c:202
+  *collision_events += g.h_totals[kTotCollisions];  // omp3/neutral.c:203
+  if (g.opt_print) {
+    printf("Particles  %llu\n", (unsigned long long)g.h_totals[kTotProcessed]);  // :205
+  }
+}
+
+void check_boundary_args(const char* who, int nx, int ny, int global_nx, int global_ny,
+                         int pad, int x_off, int y_off) {
+  if (pad != 0 || x_off != 0 || y_off != 0 || nx != global_nx || ny != global_ny) {
+    terminate("%s: only the single-rank mesh of main.c:34,42-43 is supported "
+              "(pad=%d x_off=%d y_off=%d nx=%d/%d ny=%d/%d)",
+              who, pad, x_off, y_off, nx, global_nx, ny, global_ny);
+  }
+}
+
+// problems/neutral.tests lookup: "<params_filename> result=<value>"
+bool find_expected(const char* tests_file, const char* key, double* value) {
+  FILE* fp = fopen(tests_file, "r");
+  if (!fp) return false;
+  char line[4096];
+  bool found = false;
+  while (fgets(line, sizeof(line), fp)) {
+    char name[2048];
+    int off = 0;
+    if (sscanf(line, "%2047s%n", name, &off) != 1 || name[0] == '#') continue;
+    if (strcmp(name, key) != 0) continue;
+    const char* eq = strchr(line + off, '=');
+    if (!eq) continue;
+    *value = strtod(eq + 1, nullptr);
+    found = true;
+    break;
+  }
+  fclose(fp);
+  return found;
+}
+
+__global__ void k_partial_sums(const double* __restrict__ v, size_t n, double* partial) {
+  double s = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    s += v[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ double warp_part[32];
+  if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? warp_part[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  }
+}
+
+double device_sum(const double* v, size_t n) {
+  const int blocks = 592, threads = 256;
+  double* d_partial = nullptr;
+  CU_FATAL(cudaMalloc(&d_partial, sizeof(double) * blocks));
+  k_partial_sums<<<blocks, threads, 0, g.stream>>>(v, n, d_partial);
+  g.launches++;
+  std::vector<double> h(blocks);
+  CU_FATAL(cudaMemcpyAsync(h.data(), d_partial, sizeof(double) * blocks,
+                           cudaMemcpyDeviceToHost, g.stream));
+  CU_FATAL(cudaStreamSynchronize(g.stream));
+  cudaFree(d_partial);
+  double s = 0.0;
+  for (double x : h) s += x;
+  return s;
+}
+
+}  // namespace
+
+// ======================================================================================
+// 1. plugin boundary, device-resident flavour
+// ======================================================================================
+extern "C" void solve_transport_2d(
+    const int nx, const int ny, const int global_nx, const int global_ny,
+    const uint64_t master_key, const int pad, const int x_off, const int y_off,
+    const double dt, const int ntotal_particles, int* nlocal_particles,
+    const int* neighbours, nb200_particle_soa* particles, const double* density,
+    const double* edgex, const double* edgey, const double* edgedx, const double* edgedy,
+    nb200_cross_section* cs_scatter_table, nb200_cross_section* cs_absorb_table,
+    double* energy_deposition_tally, uint64_t* reduce_array0, uint64_t* reduce_array1,
+    uint64_t* reduce_array2, uint64_t* facet_events, uint64_t* collision_events) {
+  (void)neighbours; (void)edgedx; (void)edgedy;
+  if (!(*nlocal_particles)) {  // omp3/neutral.c:30-33
+    printf("Out of particles\n");
+    return;
+  }
+  require_ready();
+  check_boundary_args("solve_transport_2d", nx, ny, global_nx, global_ny, pad, x_off, y_off);
+  Bank* bank = bank_of(particles);
+  if (!bank) terminate("solve_transport_2d: `particles` is not a bank created by this "
+                       "kernel set's inject_particles / nb200_bank_create");
+  run_step(bank, nx, ny, master_key, dt, ntotal_particles, density, edgex, edgey,
+           cs_scatter_table->keys, cs_scatter_table->values, cs_scatter_table->nentries,
+           cs_absorb_table->keys, cs_absorb_table->values, cs_absorb_table->nentries,
+           energy_deposition_tally, reduce_array0, reduce_array1, reduce_array2,
+           facet_events, collision_events);
+}
+
+extern "C" size_t inject_particles(
+    const int nparticles, const int global_nx, const int local_nx, const int local_ny,
+    const int pad, const double local_particle_left_off,
+    const double local_particle_bottom_off, const double local_particle_width,
+    const double local_particle_height, const int x_off, const int y_off, const double dt,
+    const double* edgex, const double* edgey, const double initial_energy,
+    nb200_particle_soa** particles) {
+  require_ready();
+  check_boundary_args("inject_particles", local_nx, local_ny, global_nx, local_ny, pad, x_off,
+                      y_off);
+  const int first = g.shard_count >= 0 ? g.shard_first : 0;
+  const int count = g.shard_count >= 0 ? g.shard_count : nparticles;
+  if (first < 0 || first + count > nparticles)
+    terminate("inject_particles: shard [%d, %d) outside [0, %d)", first, first + count,
+              nparticles);
+
+  // The mesh edges live in kernel-set (device) memory.
+  std::vector<double> ex(local_nx + 1), ey(local_ny + 1);
+  CU_FATAL(cudaMemcpy(ex.data(), edgex, sizeof(double) * (local_nx + 1),
+                      cudaMemcpyDeviceToHost));
+  CU_FATAL(cudaMemcpy(ey.data(), edgey, sizeof(double) * (local_ny + 1),
+                      cudaMemcpyDeviceToHost));
+
+  const size_t n = (size_t)std::max(count, 1);
+  std::vector<double> x(n), y(n), ox(n), oy(n), en(n), wt(n), dtc(n), mfp(n);
+  std::vector<int> cx(n), cy(n), dead(n);
+
+  // First cell whose half-open interval holds v; 0 when there is none - what the
+  // reference's linear scan returns (omp3/neutral.c:590-603), found by bisection.
+  auto locate = [](const std::vector<double>& edge, int ncells, double v) {
+    int lo = 0, hi = ncells;
+    if (!(v >= edge[0])) return 0;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (v >= edge[mid]) lo = mid; else hi = mid;
+    }
+    return (v >= edge[lo] && v < edge[lo + 1]) ? lo : 0;
+  };
+
+#pragma omp parallel for schedule(static)
+  for (int s = 0; s < count; ++s) {
+    const uint64_t kk = (uint64_t)(first + s);
+    double r0, r1;
+    random_pair(kk, 0, 0, r0, r1);  // omp3/neutral.c:581
+    x[s] = local_particle_left_off + r0 * local_particle_width;
+    y[s] = local_particle_bottom_off + r1 * local_particle_height;
+    cx[s] = locate(ex, local_nx, x[s]);
+    cy[s] = locate(ey, local_ny, y[s]);
+    random_pair(kk, 0, 1, r0, r1);  // omp3/neutral.c:611
+    const double theta = 2.0 * M_PI * r0;
+    ox[s] = cos(theta);
+    oy[s] = sin(theta);
+    en[s] = initial_energy;
+    wt[s] = 1.0;
+    dtc[s] = dt;
+    mfp[s] = 0.0;
+    dead[s] = 0;
+  }
+
+  size_t bytes = 0;
+  BankHandle* h = new_handle(count, (uint64_t)first, &bytes);
+  SoaView host{x.data(), y.data(), ox.data(), oy.data(), en.data(), wt.data(), dtc.data(),
+               mfp.data(), cx.data(), cy.data(), dead.data()};
+  upload_host_soa(host, count, h->impl->cur);
+  *particles = &h->view;
+  return bytes;
+}
+
+extern "C" void validate(const int nx, const int ny, const char* params_filename,
+                         const int rank, double* energy_tally) {
+  require_ready();
+  const double total = device_sum(energy_tally, (size_t)nx * ny);
+  if (rank != 0) return;
+  printf("\nFinal global_energy_tally %.15e\n", total);
+  double expected = 0.0;
+  if (!find_expected("problems/neutral.tests", params_filename, &expected)) {
+    printf("Warning. Test entry was not found, could NOT validate.\n");
+    return;
+  }
+  printf("Expected %.12e, result was %.12e.\n", expected, total);
+  const double scale = fabs(expected) > 0.0 ? fabs(expected) : 1.0;
+  if (fabs(expected - total) / scale < 1.0e-3) {  // VALIDATE_TOLERANCE, neutral_data.h:27
+    printf("PASSED validation.\n");
+  } else {
+    printf("FAILED validation.\n");
+  }
+}
+
+// ======================================================================================
+// 2. allocation layer
+// ======================================================================================
+extern "C" size_t allocate_data(double** buf, size_t len) { return device_zalloc(buf, len); }
+extern "C" size_t allocate_float_data(float** buf, size_t len) { return device_zalloc(buf, len); }
+extern "C" size_t allocate_int_data(int** buf, size_t len) { return device_zalloc(buf, len); }
+extern "C" size_t allocate_uint64_data(uint64_t** buf, size_t len) {
+  return device_zalloc(buf, len);
+}
+
+extern "C" void allocate_host_data(double** buf, size_t len) {
+  require_ready();
+  CU_FATAL(cudaMallocHost((void**)buf, sizeof(double) * (len ? len : 1)));
+  memset(*buf, 0, sizeof(double) * len);
+}
+
+extern "C" void allocate_host_float_data(float** buf, size_t len) {
+  require_ready();
+  CU_FATAL(cudaMallocHost((void**)buf, sizeof(float) * (len ? len : 1)));
+  memset(*buf, 0, sizeof(float) * len);
+}
+
+extern "C" void deallocate_data(double* buf) { cudaFree(buf); }
+extern "C" void deallocate_host_data(double* buf) { cudaFreeHost(buf); }
+
+extern "C" void copy_buffer(const size_t len, double** src, double** dst, int send) {
+  require_ready();
+  CU_FATAL(cudaMemcpyAsync(*dst, *src, sizeof(double) * len,
+                           send ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, g.stream));
+  CU_FATAL(cudaStreamSynchronize(g.stream));
+}
+
+extern "C" void move_host_buffer_to_device(const size_t len, double** src, double** dst) {
+  device_zalloc(dst, len);
+  CU_FATAL(cudaMemcpyAsync(*dst, *src, sizeof(double) * len, cudaMemcpyHostToDevice, g.stream));
+  CU_FATAL(cudaStreamSynchronize(g.stream));
+  cudaPointerAttributes attr{};
+  if (cudaPointerGetAttributes(&attr, *src) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+    cudaFreeHost(*src);
+  } else {
+    (void)cudaGetLastError();
+    free(*src);
+  }
+  *src = nullptr;
+}
+
+extern "C" void initialise_devices(int rank) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0)
+    terminate("no CUDA device available: the b200 kernel set has no CPU fallback");
+  CU_FATAL(cudaSetDevice(rank % count));
+  require_ready();
+  cudaDeviceProp prop{};
+  CU_FATAL(cudaGetDeviceProperties(&prop, rank % count));
+  printf("Rank %d using GPU %d: %s (sm_%d%d, %d SMs, %.0f GB)\n", rank, rank % count, prop.name,
+         prop.major, prop.minor, prop.multiProcessorCount,
+         (double)prop.totalGlobalMem / (1024.0 * 1024.0 * 1024.0));
+}
+
+// ======================================================================================
+// 3. host-buffer flavour
+// ======================================================================================
+extern "C" void nb200_solve_transport_2d_host(
+    const int nx, const int ny, const int global_nx, const int global_ny,
+    const uint64_t master_key, const int pad, const int x_off, const int y_off,
+    const double dt, const int ntotal_particles, int* nlocal_particles,
+    const int* neighbours, nb200_particle_aos* particles, const double* density,
+    const double* edgex, const double* edgey, const double* edgedx, const double* edgedy,
+    nb200_cross_section* cs_scatter_table, nb200_cross_section* cs_absorb_table,
+    double* energy_deposition_tally, uint64_t* reduce_array0, uint64_t* reduce_array1,
+    uint64_t* reduce_array2, uint64_t* facet_events, uint64_t* collision_events) {
+  (void)neighbours; (void)edgedx; (void)edgedy;
+  static_assert(sizeof(nb200_particle_aos) == 80, "AoS particle must be 80 bytes");
+  const int n = *nlocal_particles;
+  if (!n) {
+    printf("Out of particles\n");
+    return;
+  }
+  require_ready();
+  check_boundary_args("nb200_solve_transport_2d_host", nx, ny, global_nx, global_ny, pad,
+                      x_off, y_off);
+  const size_t ncells = (size_t)nx * ny;
+  const int s_n = cs_scatter_table->nentries, a_n = cs_absorb_table->nentries;
+
+  auto upload = [&](const void* host, size_t bytes) {
+    void* d = nullptr;
+    CU_FATAL(cudaMalloc(&d, bytes ? bytes : 1));
+    CU_FATAL(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, g.stream));
+    return d;
+  };
+  double* d_density = (double*)upload(density, sizeof(double) * ncells);
+  double* d_edgex = (double*)upload(edgex, sizeof(double) * (nx + 1));
+  double* d_edgey = (double*)upload(edgey, sizeof(double) * (ny + 1));
+  double* d_sk = (double*)upload(cs_scatter_table->keys, sizeof(double) * s_n);
+  double* d_sv = (double*)upload(cs_scatter_table->values, sizeof(double) * s_n);
+  double* d_ak = (double*)upload(cs_absorb_table->keys, sizeof(double) * a_n);
+  double* d_av = (double*)upload(cs_absorb_table->values, sizeof(double) * a_n);
+  double* d_tally = (double*)upload(energy_deposition_tally, sizeof(double) * ncells);
+  void* d_aos = upload(particles, sizeof(nb200_particle_aos) * (size_t)n);
+  uint64_t* d_r[3] = {nullptr, nullptr, nullptr};
+  uint64_t* h_r[3] = {reduce_array0, reduce_array1, reduce_array2};
+  for (int k = 0; k < 3; ++k)
+    if (h_r[k]) d_r[k] = (uint64_t*)upload(h_r[k], sizeof(uint64_t) * (size_t)n);
+
+  Bank bank;
+  bank.n = n;
+  bank.pid0 = 0;
+  bank_alloc(bank.cur, n);
+  g.launches += launch_import_aos(bank.cur, d_aos, n, g.stream);
+  g.cs_s_keys = nullptr;  // fresh uploads: never trust the cached grid comparison
+  run_step(&bank, nx, ny, master_key, dt, ntotal_particles, d_density, d_edgex, d_edgey, d_sk,
+           d_sv, s_n, d_ak, d_av, a_n, d_tally, d_r[0], d_r[1], d_r[2], facet_events,
+           collision_events);
+  g.cs_s_keys = nullptr;
+  g.launches += launch_export_aos(bank.cur, d_aos, n, g.stream);
+  CU_FATAL(cudaMemcpyAsync(particles, d_aos, sizeof(nb200_particle_aos) * (size_t)n,
+                           cudaMemcpyDeviceToHost, g.stream));
+  CU_FATAL(cudaMemcpyAsync(energy_deposition_tally, d_tally, sizeof(double) * ncells,
+                           cudaMemcpyDeviceToHost, g.stream));
+  for (int k = 0; k < 3; ++k)
+    if (h_r[k])
+      CU_FATAL(cudaMemcpyAsync(h_r[k], d_r[k], sizeof(uint64_t) * (size_t)n,
+                               cudaMemcpyDeviceToHost, g.stream));
+  CU_FATAL(cudaStreamSynchronize(g.stream));
+  bank_release(bank.cur);
+  void* to_free[] = {d_density, d_edgex, d_edgey, d_sk, d_sv, d_ak, d_av, d_tally, d_aos,
+                     d_r[0], d_r[1], d_r[2]};
+  for (void* p : to_free) cudaFree(p);
+}
+
+// ======================================================================================
+// 4. extensions
+// ======================================================================================
+extern "C" int nb200_abi_version(void) { return NB200_ABI_VERSION; }
+extern "C" const char* nb200_last_error(void) { return g.last_error.c_str(); }
+
+extern "C" int nb200_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return count;
+}
+
+extern "C" int nb200_set_stream(void* cuda_stream) {
+  g.stream = (cudaStream_t)cuda_stream;
+  return 0;
+}
+
+extern "C" int nb200_set_shard(int first, int count) {
+  g.shard_first = first;
+  g.shard_count = count;
+  return 0;
+}
+
+extern "C" int nb200_bank_create(const nb200_particle_soa* host, int count, int pid_first,
+                                 nb200_particle_soa** particles) {
+  if (ensure_ready() != 0) return -1;
+  if (!host || !particles || count < 0) {
+    set_error("nb200_bank_create: bad arguments");
+    return -3;
+  }
+  BankHandle* h = new_handle(count, (uint64_t)pid_first, nullptr);
+  if (count > 0) upload_host_soa(as_soa_view(*host), count, h->impl->cur);
+  *particles = &h->view;
+  return 0;
+}
+
+extern "C" int nb200_bank_upload(nb200_particle_soa* particles, const nb200_particle_soa* host) {
+  if (ensure_ready() != 0) return -1;
+  Bank* bank = bank_of(particles);
+  if (!bank || !host) {
+    set_error("nb200_bank_upload: not a bank handle");
+    return -3;
+  }
+  if (!bank->has_export) {
+    soa_alloc(bank->exported, bank->n);
+    bank->has_export = true;
+    reinterpret_cast<BankHandle*>(particles)->view = as_public(bank->exported);
+  }
+  // The plain SoA view doubles as the staging area: H2D per field, then one repack kernel.
+  const SoaView& s = bank->exported;
+  const size_t n = (size_t)bank->n;
+  const double* hd[] = {host->x, host->y, host->omega_x, host->omega_y, host->energy,
+                        host->weight, host->dt_to_census, host->mfp_to_collision};
+  double* dd[] = {s.x, s.y, s.omega_x, s.omega_y, s.energy, s.weight, s.dt_to_census,
+                  s.mfp_to_collision};
+  for (int k = 0; k < 8; ++k)
+    CU_TRY(cudaMemcpyAsync(dd[k], hd[k], sizeof(double) * n, cudaMemcpyHostToDevice, g.stream));
+  const int* hi[] = {host->cellx, host->celly, host->dead};
+  int* di[] = {s.cellx, s.celly, s.dead};
+  for (int k = 0; k < 3; ++k)
+    CU_TRY(cudaMemcpyAsync(di[k], hi[k], sizeof(int) * n, cudaMemcpyHostToDevice, g.stream));
+  g.launches += launch_import_soa(bank->cur, s, bank->n, 0, g.stream);
+  return 0;
+}
+
+extern "C" int nb200_accumulate(double* dst_device, const double* src_device, size_t n) {
+  if (ensure_ready() != 0) return -1;
+  g.launches += launch_accumulate(dst_device, src_device, n, g.stream);
+  return 0;
+}
+
+extern "C" int nb200_bank_export(nb200_particle_soa* particles) {
+  if (ensure_ready() != 0) return -1;
+  Bank* bank = bank_of(particles);
+  if (!bank) {
+    set_error("nb200_bank_export: not a bank handle");
+    return -3;
+  }
+  if (!bank->has_export) {
+    soa_alloc(bank->exported, bank->n);
+    bank->has_export = true;
+    reinterpret_cast<BankHandle*>(particles)->view = as_public(bank->exported);
+  }
+  g.launches += launch_export_soa(bank->cur, bank->exported, bank->n, g.stream);
+  CU_TRY(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+extern "C" int nb200_bank_download(nb200_particle_soa* particles, nb200_particle_soa* host) {
+  const int rc = nb200_bank_export(particles);
+  if (rc != 0) return rc;
+  Bank* bank = bank_of(particles);
+  const SoaView& s = bank->exported;
+  const size_t n = (size_t)bank->n;
+  const double* dd[] = {s.x, s.y, s.omega_x, s.omega_y, s.energy, s.weight, s.dt_to_census,
+                        s.mfp_to_collision};
+  double* hd[] = {host->x, host->y, host->omega_x, host->omega_y, host->energy, host->weight,
+                  host->dt_to_census, host->mfp_to_collision};
+  for (int k = 0; k < 8; ++k)
+    CU_TRY(cudaMemcpyAsync(hd[k], dd[k], sizeof(double) * n, cudaMemcpyDeviceToHost, g.stream));
+  const int* di[] = {s.cellx, s.celly, s.dead};
+  int* hi[] = {host->cellx, host->celly, host->dead};
+  for (int k = 0; k < 3; ++k)
+    CU_TRY(cudaMemcpyAsync(hi[k], di[k], sizeof(int) * n, cudaMemcpyDeviceToHost, g.stream));
+  CU_TRY(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+extern "C" int nb200_bank_copy(nb200_particle_soa* dst, nb200_particle_soa* src) {
+  if (ensure_ready() != 0) return -1;
+  Bank* d = bank_of(dst);
+  Bank* s = bank_of(src);
+  if (!d || !s || d->n != s->n) {
+    set_error("nb200_bank_copy: handles must be banks of the same size");
+    return -3;
+  }
+  const size_t n = (size_t)s->n;
+  CU_TRY(cudaMemcpyAsync(d->cur.pos, s->cur.pos, sizeof(double2) * n, cudaMemcpyDeviceToDevice, g.stream));
+  CU_TRY(cudaMemcpyAsync(d->cur.dir, s->cur.dir, sizeof(double2) * n, cudaMemcpyDeviceToDevice, g.stream));
+  CU_TRY(cudaMemcpyAsync(d->cur.ew, s->cur.ew, sizeof(double2) * n, cudaMemcpyDeviceToDevice, g.stream));
+  CU_TRY(cudaMemcpyAsync(d->cur.tm, s->cur.tm, sizeof(double2) * n, cudaMemcpyDeviceToDevice, g.stream));
+  CU_TRY(cudaMemcpyAsync(d->cur.meta, s->cur.meta, sizeof(int4) * n, cudaMemcpyDeviceToDevice, g.stream));
+  d->pid0 = s->pid0;
+  return 0;
+}
+
+extern "C" int nb200_bank_size(nb200_particle_soa* particles) {
+  Bank* bank = bank_of(particles);
+  return bank ? bank->n : -3;
+}
+
+extern "C" int nb200_bank_free(nb200_particle_soa* particles) {
+  Bank* bank = bank_of(particles);
+  if (!bank) return -3;
+  bank_release(bank->cur);
+  if (bank->has_export) soa_release(bank->exported);
+  BankHandle* h = reinterpret_cast<BankHandle*>(particles);
+  h->magic = 0;
+  delete bank;
+  free(h);
+  return 0;
+}
+
+extern "C" int nb200_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes) {
+  if (ensure_ready() != 0) return -1;
+  CU_TRY(cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, g.stream));
+  CU_TRY(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+extern "C" int nb200_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes) {
+  if (ensure_ready() != 0) return -1;
+  CU_TRY(cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, g.stream));
+  CU_TRY(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+extern "C" int nb200_memset_d(void* dst_device, int value, size_t bytes) {
+  if (ensure_ready() != 0) return -1;
+  CU_TRY(cudaMemsetAsync(dst_device, value, bytes, g.stream));
+  return 0;
+}
+
+extern "C" int nb200_synchronize(void) {
+  if (ensure_ready() != 0) return -1;
+  CU_TRY(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+extern "C" int nb200_set_option(const char* name, int value) {
+  int* slot = nullptr;
+  if (strcmp(name, "print") == 0) slot = &g.opt_print;
+  else if (strcmp(name, "pipeline") == 0) slot = &g.opt_pipeline;
+  if (!slot) {
+    set_error("nb200_set_option: unknown option '%s'", name);
+    return -3;
+  }
+  const int prev = *slot;
+  *slot = value;
+  return prev;
+}
+
+extern "C" int nb200_last_step_stats(uint64_t out[8]) {
+  for (int k = 0; k < 8; ++k) out[k] = g.last_stats[k];
+  return 0;
+}
+
+extern "C" uint64_t nb200_kernel_launches(void) { return g.launches; }
+
+extern "C" int nb200_selftest_rng_log(uint64_t pkey0, uint64_t master_key, uint64_t counter,
+                                      int n, uint64_t* raw_host, double* unit_host,
+                                      double* neglog_host) {
+  if (ensure_ready() != 0) return -1;
+  uint64_t* d_raw = nullptr;
+  double *d_unit = nullptr, *d_nl = nullptr;
+  CU_TRY(cudaMalloc(&d_raw, sizeof(uint64_t) * 2 * n));
+  CU_TRY(cudaMalloc(&d_unit, sizeof(double) * 2 * n));
+  CU_TRY(cudaMalloc(&d_nl, sizeof(double) * 2 * n));
+  g.launches += launch_selftest_rng_log(pkey0, master_key, counter, n, g.d_logt, d_raw, d_unit,
+                                        d_nl, g.stream);
+  CU_TRY(cudaMemcpyAsync(raw_host, d_raw, sizeof(uint64_t) * 2 * n, cudaMemcpyDeviceToHost, g.stream));
+  CU_TRY(cudaMemcpyAsync(unit_host, d_unit, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, g.stream));
+  CU_TRY(cudaMemcpyAsync(neglog_host, d_nl, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, g.stream));
+  CU_TRY(cudaStreamSynchronize(g.stream));
+  cudaFree(d_raw);
+  cudaFree(d_unit);
+  cudaFree(d_nl);
+  return 0;
+}
+
+extern "C" int nb200_selftest_log(const double* x_host, double* y_host, int n) {
+  if (ensure_ready() != 0) return -1;
+  double *d_x = nullptr, *d_y = nullptr;
+  CU_TRY(cudaMalloc(&d_x, sizeof(double) * n));
+  CU_TRY(cudaMalloc(&d_y, sizeof(double) * n));
+  CU_TRY(cudaMemcpyAsync(d_x, x_host, sizeof(double) * n, cudaMemcpyHostToDevice, g.stream));
+  g.launches += launch_selftest_log(d_x, d_y, n, g.d_logt, g.stream);
+  CU_TRY(cudaMemcpyAsync(y_host, d_y, sizeof(double) * n, cudaMemcpyDeviceToHost, g.stream));
+  CU_TRY(cudaStreamSynchronize(g.stream));
+  cudaFree(d_x);
+  cudaFree(d_y);
+  return 0;
+}
+
+extern "C" int nb200_selftest_cs(const double* keys_host, const double* values_host,
+                                 int nentries, const double* energies_host, int n,
+                                 int* index_host, double* value_host) {
+  if (ensure_ready() != 0) return -1;
+  double *d_k = nullptr, *d_v = nullptr, *d_e = nullptr, *d_o = nullptr;
+  int* d_i = nullptr;
+  CU_TRY(cudaMalloc(&d_k, sizeof(double) * nentries));
+  CU_TRY(cudaMalloc(&d_v, sizeof(double) * nentries));
+  CU_TRY(cudaMalloc(&d_e, sizeof(double) * n));
+  CU_TRY(cudaMalloc(&d_o, sizeof(double) * n));
+  CU_TRY(cudaMalloc(&d_i, sizeof(int) * n));
+  CU_TRY(cudaMemcpyAsync(d_k, keys_host, sizeof(double) * nentries, cudaMemcpyHostToDevice, g.stream));
+  CU_TRY(cudaMemcpyAsync(d_v, values_host, sizeof(double) * nentries, cudaMemcpyHostToDevice, g.stream));
+  CU_TRY(cudaMemcpyAsync(d_e, energies_host, sizeof(double) * n, cudaMemcpyHostToDevice, g.stream));
+  g.launches += launch_selftest_cs(d_k, d_v, nentries, d_e, n, d_i, d_o, g.stream);
+  CU_TRY(cudaMemcpyAsync(index_host, d_i, sizeof(int) * n, cudaMemcpyDeviceToHost, g.stream));
+  CU_TRY(cudaMemcpyAsync(value_host, d_o, sizeof(double) * n, cudaMemcpyDeviceToHost, g.stream));
+  CU_TRY(cudaStreamSynchronize(g.stream));
+  cudaFree(d_k); cudaFree(d_v); cudaFree(d_e); cudaFree(d_o); cudaFree(d_i);
+  return 0;
+}
+
+extern "C" void nb200_host_threefry2x64_20(uint64_t c0, uint64_t c1, uint64_t k0, uint64_t k1,
+                                           uint64_t out[2]) {
+  threefry2x64_20(c0, c1, k0, k1, out[0], out[1]);
+}
+
+extern "C" double nb200_host_log(double x) { return nb_log(x, &kHostLogTable); }

@@ -1,0 +1,75 @@
+// nb_bank.cuh - device layout of a particle bank and the argument block of one timestep.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nb_math.cuh"
+
+namespace nb {
+
+// Packed-pair SoA: every per-particle access is one 16-byte vector load/store that is
+// coalesced across the warp (32 lanes x 16 B = 512 contiguous bytes per field pair).
+// The fields are those of the reference's Particle (neutral_data.h:48-79):
+//   pos  = (x, y)                      dir = (omega_x, omega_y)
+//   ew   = (energy, weight)            tm  = (dt_to_census, mfp_to_collision)
+//   meta = (cellx, celly, dead, origin)
+// `origin` is the particle's index in injection order (global pid = pid0 + origin): the RNG
+// key must follow a particle through any reordering of the bank (omp3/neutral.c:89,632-641).
+struct BankView {
+  double2* pos;
+  double2* dir;
+  double2* ew;
+  double2* tm;
+  int4* meta;
+};
+
+constexpr size_t kBankBytesPerParticle = 4 * sizeof(double2) + sizeof(int4);  // 80
+
+// Plain 11-array SoA, the reference's -DSoA Particle (neutral_data.h:48-61). Used for
+// import/export at the plugin boundary only.
+struct SoaView {
+  double* x;
+  double* y;
+  double* omega_x;
+  double* omega_y;
+  double* energy;
+  double* weight;
+  double* dt_to_census;
+  double* mfp_to_collision;
+  int* cellx;
+  int* celly;
+  int* dead;
+};
+
+// Step totals, one 64-bit counter each (device memory, zeroed by the host per step).
+enum { kTotFacets = 0, kTotCollisions, kTotProcessed, kTotCensus, kTotDeaths, kTotCount = 8 };
+
+struct StepArgs {
+  int nx, ny;  // mesh cells (pad = 0, offsets = 0: the only configuration main.c produces)
+  int n;       // bank slots to visit
+  uint64_t master_key;
+  uint64_t pid0;  // global pid of origin 0 (particle sharding across GPUs)
+  double dt;
+  double inv_ntotal;
+  const double* density;
+  const double* edgex;
+  const double* edgey;
+  const double* s_keys;
+  const double* s_vals;
+  const double* a_keys;
+  const double* a_vals;
+  int s_n, a_n;
+  int same_keys;  // both tables share one energy grid (bitwise): one search serves both
+  double* tally;
+  // Per-particle cumulative event counters indexed by origin (the interface's three
+  // uint64[nparticles] scratch arrays, neutral_interface.h:19); may be null.
+  unsigned long long* p_facets;
+  unsigned long long* p_collisions;
+  unsigned long long* p_census;
+  unsigned long long* totals;
+  BankView bank;
+  const LogTable* logt;
+};
+
+}  // namespace nb

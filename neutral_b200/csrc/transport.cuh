@@ -1,0 +1,28 @@
+// transport.cuh - internal C++ interface between the C-ABI layer and the kernels.
+#pragma once
+
+#include "nb_bank.cuh"
+
+namespace nb {
+
+constexpr int kHistoryThreads = 128;
+
+// Every launch_* returns the number of kernels it launched (for the launch counter).
+int launch_history_direct(const StepArgs& a, cudaStream_t st);
+
+int launch_import_soa(BankView b, SoaView s, int n, int origin0, cudaStream_t st);
+int launch_export_soa(BankView b, SoaView s, int n, cudaStream_t st);
+int launch_import_aos(BankView b, const void* aos, int n, cudaStream_t st);
+int launch_export_aos(BankView b, void* aos, int n, cudaStream_t st);
+
+int launch_accumulate(double* dst, const double* src, size_t n, cudaStream_t st);
+
+int launch_selftest_rng_log(uint64_t pkey0, uint64_t master_key, uint64_t counter, int n,
+                            const LogTable* logt, uint64_t* raw, double* unit,
+                            double* neglog, cudaStream_t st);
+int launch_selftest_log(const double* x, double* y, int n, const LogTable* logt,
+                        cudaStream_t st);
+int launch_selftest_cs(const double* keys, const double* vals, int n_entries, const double* e,
+                       int n, int* ind, double* out, cudaStream_t st);
+
+}  // namespace nb
