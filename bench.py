@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--particles", type=int, default=0, help="override particles per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--opts", default="", help="library options, e.g. pipeline=0,fast_div=0")
     return ap.parse_args()
 
 
@@ -244,6 +245,11 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
     lib = load_library(build=False)
     lib.initialise_devices.restype = None
     lib.nb200_set_option(b"print", 0)
+    opts = dict(kv.split("=") for kv in args.opts.split(",") if kv)
+    for k, v in opts.items():
+        if lib.nb200_set_option(k.encode(), int(v)) < -1:
+            sys.exit(f"unknown library option {k}")
+    pipeline = int(opts.get("pipeline", 1))
 
     deck = load_deck(args.deck)
     per_gpu = args.particles or deck.nparticles
@@ -303,6 +309,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
 
     events = sum(r.events for r in timed)
     kernel_ns = sum(r.kernel_ns for r in timed)
+    sort_ns = sum(r.sort_ns for r in timed)
     hist_launches = len(timed)
     alg_bytes = algorithmic_bytes(timed)
     tally_sum = float(torch.from_numpy(sim.tally_to_host()).sum()) if rank == 0 else 0.0
@@ -380,12 +387,14 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
     # dominant kernel = the history kernel; per-launch figures of THIS rank (rank 0)
     ach_gbs = (alg_bytes / max(kernel_ns, 1))  # bytes per ns == GB/s
     roofline = {
-        "bound": "hbm", "kernel": "k_history_direct", "achieved": ach_gbs, "peak": peak,
+        "bound": "hbm", "kernel": "k_history" if pipeline else "k_history_direct",
+        "achieved": ach_gbs, "peak": peak,
         "unit": "GB/s", "frac": ach_gbs / peak, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes / max(hist_launches, 1),
         "avg_launch_ms": kernel_ns / max(hist_launches, 1) / 1e6,
         "launches_timed": hist_launches,
         "kernel_share_of_step": (kernel_ns / 1e6) / max(elapsed_ms, 1e-9),
+        "sort_phase_share_of_step": (sort_ns / 1e6) / max(elapsed_ms, 1e-9),
         "traffic": ncu_traffic_per_launch(deck.name),
     }
     line = {
@@ -400,6 +409,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
                                 f"{2 * ncells * 8 / 2**20:.0f} MiB, random access)",
                    "parallelism": f"particle-sharded x{world}, NCCL all-reduce of the tally "
                                   "delta per timestep" if world > 1 else "single GPU",
+                   "options": args.opts or "defaults (pipeline=1,fast_div=1,tile_shift=4)",
                    "events_per_step": events_all / args.steps,
                    "tally_sum": tally_sum},
         "roofline": roofline,

@@ -184,14 +184,18 @@ int nb200_synchronize(void);
  * (after the all-reduce of the deltas). */
 int nb200_accumulate(double* dst_device, const double* src_device, size_t n);
 
-/* Options: "print" (1: print the reference's "Particles" line), "pipeline"
- * (0: direct one-thread-per-history kernel, 1: phased pipeline - default).
+/* Options: "print" (1: print the reference's "Particles" line); "pipeline" (1, default:
+ * phased timestep - begin-step/classify, counting sort by next-event type and tile, event
+ * loop; 0: the direct one-thread-per-history kernel on the unsorted bank); "fast_div"
+ * (1, default: exact division by loop-invariant divisors through their reciprocals);
+ * "tile_shift" (log2 of the sort tile edge in cells, default 4; < 0: sort by class only).
  * Returns the previous value, or a negative code for an unknown name. */
 int nb200_set_option(const char* name, int value);
 
 /* Statistics of the most recent solve_transport_2d: out[0..4] = facets, collisions,
  * particles processed, census events, deaths; out[5] = kernels launched by that call;
- * out[6] = nanoseconds the step's history kernels took on the stream (CUDA events). */
+ * out[6] = nanoseconds the step's history kernel took on the stream (CUDA events);
+ * out[7] = nanoseconds of the sort phase in front of it. */
 int nb200_last_step_stats(uint64_t out[8]);
 /* Kernels launched by this library since load (monotonic). */
 uint64_t nb200_kernel_launches(void);
@@ -202,6 +206,9 @@ uint64_t nb200_kernel_launches(void);
 int nb200_selftest_rng_log(uint64_t pkey0, uint64_t master_key, uint64_t counter, int n,
                            uint64_t* raw_host, double* unit_host, double* neglog_host);
 int nb200_selftest_log(const double* x_host, double* y_host, int n);
+/* fast[i] = a/b through the kernels' reciprocal-based exact division, ieee[i] = a/b. */
+int nb200_selftest_div(const double* a_host, const double* b_host, int n, double* fast_host,
+                       double* ieee_host);
 int nb200_selftest_cs(const double* keys_host, const double* values_host, int nentries,
                       const double* energies_host, int n, int* index_host,
                       double* value_host);

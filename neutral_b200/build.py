@@ -14,8 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libneutral_b200.so")
-SOURCES = ["transport.cu", "capi.cu"]
-HEADERS = ["transport.cuh", "nb_bank.cuh", "nb_math.cuh", "glibc_log_table.inc",
+SOURCES = ["transport.cu", "pipeline.cu", "capi.cu"]
+HEADERS = ["transport.cuh", "nb_device.cuh", "nb_bank.cuh", "nb_math.cuh", "glibc_log_table.inc",
            os.path.join("..", "..", "include", "neutral_b200.h")]
 
 NVCC_FLAGS = [

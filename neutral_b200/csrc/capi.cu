@@ -30,7 +30,11 @@ constexpr uint64_t kBankMagic = 0x6e62323030424e4bull;  // "nb200BNK"
 
 struct Bank {
   BankView cur{};
+  BankView alt{};  // double buffer of the per-step sort (allocated on first use)
+  bool has_alt = false;
+  unsigned* keys = nullptr;
   int n = 0;
+  int n_upper = 0;  // slots [n_upper, n) are known to hold dead particles
   uint64_t pid0 = 0;
   SoaView exported{};  // lazily allocated plain SoA view (11 arrays)
   bool has_export = false;
@@ -51,7 +55,12 @@ struct Context {
   LogTable* d_logt = nullptr;
   unsigned long long* d_totals = nullptr;
   unsigned long long* h_totals = nullptr;  // pinned
-  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // bracket the history kernels of a step
+  cudaEvent_t ev_begin = nullptr, ev_mid = nullptr, ev_end = nullptr;  // phase timing
+  unsigned* d_bins = nullptr;  // histogram + cursors of the per-step sort
+  unsigned* d_n_live = nullptr;
+  int bins_capacity = 0;
+  int opt_fast_div = 1;
+  int opt_tile_shift = 4;
   uint64_t launches = 0;
   uint64_t last_stats[8] = {0};
   int opt_print = 1;
@@ -123,7 +132,9 @@ int ensure_ready() {
   CU_TRY(cudaMalloc(&g.d_totals, sizeof(unsigned long long) * kTotCount));
   CU_TRY(cudaMallocHost(&g.h_totals, sizeof(unsigned long long) * kTotCount));
   CU_TRY(cudaEventCreate(&g.ev_begin));
+  CU_TRY(cudaEventCreate(&g.ev_mid));
   CU_TRY(cudaEventCreate(&g.ev_end));
+  CU_TRY(cudaMalloc(&g.d_n_live, sizeof(unsigned)));
   g.ready = true;
   return 0;
 }
@@ -200,6 +211,7 @@ BankHandle* new_handle(int n, uint64_t pid0, size_t* bytes) {
   h->impl = new Bank();
   h->magic = kBankMagic;
   h->impl->n = n;
+  h->impl->n_upper = n;
   h->impl->pid0 = pid0;
   const size_t b = bank_alloc(h->impl->cur, n);
   if (bytes) *bytes = b;
@@ -286,18 +298,54 @@ void run_step(Bank* bank, int nx, int ny, uint64_t master_key, double dt, int nt
 
   CU_FATAL(cudaMemsetAsync(g.d_totals, 0, sizeof(unsigned long long) * kTotCount, g.stream));
   CU_FATAL(cudaEventRecord(g.ev_begin, g.stream));
-  g.launches += launch_history_direct(a, g.stream);
+  if (g.opt_pipeline) {
+    // P1-P3: begin-step set-up, classification and counting sort into the double buffer
+    SortArgs s{};
+    s.tile_shift = g.opt_tile_shift;
+    s.tiles_x = s.tile_shift >= 0 ? ((nx - 1) >> s.tile_shift) + 1 : 1;
+    s.ntiles = s.tile_shift >= 0 ? s.tiles_x * (((ny - 1) >> s.tile_shift) + 1) : 1;
+    s.nbins = 3 * s.ntiles + 1;
+    s.n_upper = bank->n_upper;
+    s.n = bank->n;
+    if (!bank->has_alt) {
+      bank_alloc(bank->alt, bank->n);
+      device_zalloc(&bank->keys, (size_t)bank->n);
+      bank->has_alt = true;
+    }
+    if (g.bins_capacity < s.nbins) {
+      cudaFree(g.d_bins);
+      CU_FATAL(cudaMalloc(&g.d_bins, sizeof(unsigned) * 2 * (size_t)s.nbins));
+      g.bins_capacity = s.nbins;
+    }
+    s.keys = bank->keys;
+    s.bin_count = g.d_bins;
+    s.bin_cursor = g.d_bins + s.nbins;
+    s.n_live = g.d_n_live;
+    g.launches += launch_sort_phase(a, s, bank->alt, g.stream);
+    std::swap(bank->cur, bank->alt);
+    a.bank = bank->cur;
+    CU_FATAL(cudaEventRecord(g.ev_mid, g.stream));
+    // P4: event loop over the sorted live prefix
+    g.launches += launch_history(a, g.d_n_live, s.n_upper, g.opt_fast_div != 0, g.stream);
+  } else {
+    CU_FATAL(cudaEventRecord(g.ev_mid, g.stream));
+    g.launches += launch_history_direct(a, g.stream);
+  }
   CU_FATAL(cudaGetLastError());
   CU_FATAL(cudaEventRecord(g.ev_end, g.stream));
   CU_FATAL(cudaMemcpyAsync(g.h_totals, g.d_totals, sizeof(unsigned long long) * kTotCount,
                            cudaMemcpyDeviceToHost, g.stream));
   CU_FATAL(cudaStreamSynchronize(g.stream));
+  if (g.opt_pipeline)  // everything behind the survivors of this step is dead from now on
+    bank->n_upper = (int)(g.h_totals[kTotProcessed] - g.h_totals[kTotDeaths]);
 
   for (int k = 0; k < kTotCount; ++k) g.last_stats[k] = g.h_totals[k];
   g.last_stats[5] = g.launches - launches0;
   float kernel_ms = 0.0f;
-  CU_FATAL(cudaEventElapsedTime(&kernel_ms, g.ev_begin, g.ev_end));
-  g.last_stats[6] = (uint64_t)((double)kernel_ms * 1.0e6);  // ns on the launching stream
+  CU_FATAL(cudaEventElapsedTime(&kernel_ms, g.ev_mid, g.ev_end));
+  g.last_stats[6] = (uint64_t)((double)kernel_ms * 1.0e6);  // history kernel, ns on the stream
+  CU_FATAL(cudaEventElapsedTime(&kernel_ms, g.ev_begin, g.ev_mid));
+  g.last_stats[7] = (uint64_t)((double)kernel_ms * 1.0e6);  // sort phase, ns
   *facet_events += g.h_totals[kTotFacets];          // omp3/neutral.c:202
   *collision_events += g.h_totals[kTotCollisions];  // omp3/neutral.c:203
   if (g.opt_print) {
@@ -594,6 +642,7 @@ extern "C" void nb200_solve_transport_2d_host(
 
   Bank bank;
   bank.n = n;
+  bank.n_upper = n;
   bank.pid0 = 0;
   bank_alloc(bank.cur, n);
   g.launches += launch_import_aos(bank.cur, d_aos, n, g.stream);
@@ -613,6 +662,10 @@ extern "C" void nb200_solve_transport_2d_host(
                                cudaMemcpyDeviceToHost, g.stream));
   CU_FATAL(cudaStreamSynchronize(g.stream));
   bank_release(bank.cur);
+  if (bank.has_alt) {
+    bank_release(bank.alt);
+    cudaFree(bank.keys);
+  }
   void* to_free[] = {d_density, d_edgex, d_edgey, d_sk, d_sv, d_ak, d_av, d_tally, d_aos,
                      d_r[0], d_r[1], d_r[2]};
   for (void* p : to_free) cudaFree(p);
@@ -683,6 +736,7 @@ extern "C" int nb200_bank_upload(nb200_particle_soa* particles, const nb200_part
   for (int k = 0; k < 3; ++k)
     CU_TRY(cudaMemcpyAsync(di[k], hi[k], sizeof(int) * n, cudaMemcpyHostToDevice, g.stream));
   g.launches += launch_import_soa(bank->cur, s, bank->n, 0, g.stream);
+  bank->n_upper = bank->n;
   return 0;
 }
 
@@ -744,6 +798,7 @@ extern "C" int nb200_bank_copy(nb200_particle_soa* dst, nb200_particle_soa* src)
   CU_TRY(cudaMemcpyAsync(d->cur.tm, s->cur.tm, sizeof(double2) * n, cudaMemcpyDeviceToDevice, g.stream));
   CU_TRY(cudaMemcpyAsync(d->cur.meta, s->cur.meta, sizeof(int4) * n, cudaMemcpyDeviceToDevice, g.stream));
   d->pid0 = s->pid0;
+  d->n_upper = s->n_upper;
   return 0;
 }
 
@@ -756,6 +811,10 @@ extern "C" int nb200_bank_free(nb200_particle_soa* particles) {
   Bank* bank = bank_of(particles);
   if (!bank) return -3;
   bank_release(bank->cur);
+  if (bank->has_alt) {
+    bank_release(bank->alt);
+    cudaFree(bank->keys);
+  }
   if (bank->has_export) soa_release(bank->exported);
   BankHandle* h = reinterpret_cast<BankHandle*>(particles);
   h->magic = 0;
@@ -794,6 +853,8 @@ extern "C" int nb200_set_option(const char* name, int value) {
   int* slot = nullptr;
   if (strcmp(name, "print") == 0) slot = &g.opt_print;
   else if (strcmp(name, "pipeline") == 0) slot = &g.opt_pipeline;
+  else if (strcmp(name, "fast_div") == 0) slot = &g.opt_fast_div;
+  else if (strcmp(name, "tile_shift") == 0) slot = &g.opt_tile_shift;
   if (!slot) {
     set_error("nb200_set_option: unknown option '%s'", name);
     return -3;
@@ -864,6 +925,21 @@ extern "C" int nb200_selftest_cs(const double* keys_host, const double* values_h
   CU_TRY(cudaMemcpyAsync(value_host, d_o, sizeof(double) * n, cudaMemcpyDeviceToHost, g.stream));
   CU_TRY(cudaStreamSynchronize(g.stream));
   cudaFree(d_k); cudaFree(d_v); cudaFree(d_e); cudaFree(d_o); cudaFree(d_i);
+  return 0;
+}
+
+extern "C" int nb200_selftest_div(const double* a_host, const double* b_host, int n,
+                                  double* fast_host, double* ieee_host) {
+  if (ensure_ready() != 0) return -1;
+  double* d[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (auto& p : d) CU_TRY(cudaMalloc(&p, sizeof(double) * n));
+  CU_TRY(cudaMemcpyAsync(d[0], a_host, sizeof(double) * n, cudaMemcpyHostToDevice, g.stream));
+  CU_TRY(cudaMemcpyAsync(d[1], b_host, sizeof(double) * n, cudaMemcpyHostToDevice, g.stream));
+  g.launches += launch_selftest_div(d[0], d[1], d[2], d[3], n, g.stream);
+  CU_TRY(cudaMemcpyAsync(fast_host, d[2], sizeof(double) * n, cudaMemcpyDeviceToHost, g.stream));
+  CU_TRY(cudaMemcpyAsync(ieee_host, d[3], sizeof(double) * n, cudaMemcpyDeviceToHost, g.stream));
+  CU_TRY(cudaStreamSynchronize(g.stream));
+  for (auto& p : d) cudaFree(p);
   return 0;
 }
 

@@ -72,4 +72,18 @@ struct StepArgs {
   const LogTable* logt;
 };
 
+// Scratch of the per-step counting sort (pipeline.cu).
+struct SortArgs {
+  unsigned* keys;        // [n] sort key of every slot in [0, n_upper)
+  unsigned* bin_count;   // [nbins] histogram
+  unsigned* bin_cursor;  // [nbins] running destination of every bin
+  unsigned* n_live;      // device scalar: slots in front of the dead bin after the sort
+  int nbins;             // 3 classes x ntiles + 1 dead bin
+  int ntiles;
+  int tiles_x;
+  int tile_shift;        // cells per tile edge = 1 << tile_shift; < 0: one tile
+  int n_upper;           // host-known upper bound of the live prefix
+  int n;                 // bank size
+};
+
 }  // namespace nb

@@ -11,44 +11,9 @@
 // Arithmetic contract: compiled with -fmad=false; expression order as in the reference
 //  so that every particle field replays bit-identically.
 #include "transport.cuh"
+#include "nb_device.cuh"
 
 namespace nb {
-
-// --------------------------------------------------------------------------------------
-// Cross-section lookup: index `ind` with keys[ind] <= e < keys[ind+1] and the linear
-// interpolation of omp3/neutral.c:514-516. The bracketing interval of a strictly increasing
-// grid is unique, so bisection finds the reference's `ind`.
-// --------------------------------------------------------------------------------------
-__device__ __forceinline__ int cs_bracket(const double* __restrict__ keys, int n, double e) {
-  int lo = 0, hi = n - 1;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (e < __ldg(keys + mid)) hi = mid; else lo = mid;
-  }
-  return lo;
-}
-
-__device__ __forceinline__ double cs_interp(const double* __restrict__ keys,
-                                            const double* __restrict__ vals, int ind,
-                                            double e) {
-  const double k0 = __ldg(keys + ind), k1 = __ldg(keys + ind + 1);
-  const double v0 = __ldg(vals + ind), v1 = __ldg(vals + ind + 1);
-  return v0 + ((e - k0) / (k1 - k0)) * (v1 - v0);
-}
-
-__device__ __forceinline__ void cs_lookup_pair(const StepArgs& a, double e, double& sig_s,
-                                               double& sig_a) {
-  const int is = cs_bracket(a.s_keys, a.s_n, e);
-  sig_s = cs_interp(a.s_keys, a.s_vals, is, e);
-  const int ia = a.same_keys ? is : cs_bracket(a.a_keys, a.a_n, e);
-  sig_a = cs_interp(a.a_keys, a.a_vals, ia, e);
-}
-
-__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 // --------------------------------------------------------------------------------------
 // k_history_direct: one thread follows one particle from the start of the timestep to its
@@ -196,19 +161,7 @@ __global__ void __launch_bounds__(kHistoryThreads) k_history_direct(const StepAr
     if (a.p_census) a.p_census[m.w] += nz;
   }
 
-  // Event totals: shuffle-reduce per warp, one 64-bit atomic per warp and counter.
-  nf = warp_sum(nf);
-  nc = warp_sum(nc);
-  np = warp_sum(np);
-  nz = warp_sum(nz);
-  nd_ = warp_sum(nd_);
-  if ((threadIdx.x & 31) == 0) {
-    if (nf) atomicAdd(a.totals + kTotFacets, nf);
-    if (nc) atomicAdd(a.totals + kTotCollisions, nc);
-    if (np) atomicAdd(a.totals + kTotProcessed, np);
-    if (nz) atomicAdd(a.totals + kTotCensus, nz);
-    if (nd_) atomicAdd(a.totals + kTotDeaths, nd_);
-  }
+  flush_totals(a.totals, nf, nc, np, nz, nd_);
 }
 
 // --------------------------------------------------------------------------------------

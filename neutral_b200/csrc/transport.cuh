@@ -10,6 +10,15 @@ constexpr int kHistoryThreads = 128;
 // Every launch_* returns the number of kernels it launched (for the launch counter).
 int launch_history_direct(const StepArgs& a, cudaStream_t st);
 
+// Phased pipeline (pipeline.cu): sort phase = begin-step/classify + scan + scatter into
+// `alt`; history = event loop over the sorted live prefix.
+int launch_sort_phase(const StepArgs& a, const SortArgs& s, const BankView& alt,
+                      cudaStream_t st);
+int launch_history(const StepArgs& a, const unsigned* n_live, int n_upper, bool fast_div,
+                   cudaStream_t st);
+int launch_selftest_div(const double* a, const double* b, double* fast, double* ieee, int n,
+                        cudaStream_t st);
+
 int launch_import_soa(BankView b, SoaView s, int n, int origin0, cudaStream_t st);
 int launch_export_soa(BankView b, SoaView s, int n, cudaStream_t st);
 int launch_import_aos(BankView b, const void* aos, int n, cudaStream_t st);

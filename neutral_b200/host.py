@@ -47,7 +47,7 @@ EXPORTED_SYMBOLS = [
     "nb200_bank_upload", "nb200_accumulate", "nb200_bank_copy", "nb200_bank_size", "nb200_bank_free", "nb200_memcpy_h2d",
     "nb200_memcpy_d2h", "nb200_memset_d", "nb200_synchronize", "nb200_set_option",
     "nb200_last_step_stats", "nb200_kernel_launches", "nb200_selftest_rng_log",
-    "nb200_selftest_log", "nb200_selftest_cs", "nb200_host_threefry2x64_20",
+    "nb200_selftest_log", "nb200_selftest_div", "nb200_selftest_cs", "nb200_host_threefry2x64_20",
     "nb200_host_log",
 ]
 
@@ -108,6 +108,7 @@ def load_library(build: bool = False) -> C.CDLL:
     L.nb200_selftest_rng_log.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, _u64p,
                                          _dp, _dp]
     L.nb200_selftest_log.argtypes = [_dp, _dp, C.c_int]
+    L.nb200_selftest_div.argtypes = [_dp, _dp, C.c_int, _dp, _dp]
     L.nb200_selftest_cs.argtypes = [_dp, _dp, C.c_int, _dp, C.c_int, _ip, _dp]
     L.nb200_host_threefry2x64_20.argtypes = [C.c_uint64] * 4 + [_u64p]
     L.nb200_host_log.argtypes = [C.c_double]
@@ -180,6 +181,7 @@ class StepResult:
     deaths: int
     launches: int
     kernel_ns: int = 0
+    sort_ns: int = 0
 
     @property
     def events(self) -> int:
@@ -271,7 +273,7 @@ class Simulation:
         self.lib.nb200_last_step_stats(stats)
         assert stats[0] == facets.value and stats[1] == colls.value
         return StepResult(int(stats[0]), int(stats[1]), int(stats[2]), int(stats[3]),
-                          int(stats[4]), int(stats[5]), int(stats[6]))
+                          int(stats[4]), int(stats[5]), int(stats[6]), int(stats[7]))
 
     def run(self, iterations: Optional[int] = None) -> List[StepResult]:
         n = self.problem.deck.iterations if iterations is None else iterations

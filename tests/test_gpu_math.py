@@ -95,3 +95,25 @@ def test_device_cross_section_brackets(gpu_lib, port):
     for i in range(len(e)):
         assert ind[i] == port.cs_index(keys, float(e[i]))
         assert out[i] == port.cs_lookup(keys, values, float(e[i]))
+
+
+def test_reciprocal_division_is_ieee_division(gpu_lib):
+    """The event loop divides by loop-invariant divisors (speed, cell mean free path) through
+    their correctly rounded reciprocals with a Markstein correction step; the quotient must
+    be the IEEE quotient bit for bit, over the operand ranges the decks produce and beyond."""
+    rng = np.random.default_rng(99)
+    n = 8_000_000
+    a = np.concatenate([
+        10.0 ** rng.uniform(-16, 1, n // 2) * rng.choice([-1.0, 1.0], n // 2),
+        rng.random(n // 4), 10.0 ** rng.uniform(-300, 300, n // 8),
+        (1.0 + rng.integers(0, 2 ** 20, n // 8) * 2.0 ** -52)])          # mantissas near 1
+    b = np.concatenate([
+        10.0 ** rng.uniform(-6, 31, n // 2),                              # 1/Sigma_t and speeds
+        10.0 ** rng.uniform(3, 8, n // 4), 10.0 ** rng.uniform(-300, 300, n // 8),
+        (2.0 - rng.integers(1, 2 ** 20, n // 8) * 2.0 ** -52)])          # mantissas near 2
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    fast, ieee = np.zeros_like(a), np.zeros_like(a)
+    assert gpu_lib.nb200_selftest_div(a.ctypes.data_as(_dp), b.ctypes.data_as(_dp), len(a),
+                                      fast.ctypes.data_as(_dp), ieee.ctypes.data_as(_dp)) == 0
+    assert np.array_equal(ieee.view(np.uint64), (a / b).view(np.uint64))  # device == host IEEE
+    assert np.array_equal(fast.view(np.uint64), ieee.view(np.uint64))

@@ -28,8 +28,27 @@ def _hashes(bank):
             for k in ALL_FIELDS]
 
 
+MODES = {
+    "pipeline": dict(pipeline=1, fast_div=1, tile_shift=4),      # the default
+    "pipeline-ieee-div": dict(pipeline=1, fast_div=0, tile_shift=2),
+    "pipeline-class-only": dict(pipeline=1, fast_div=1, tile_shift=-1),
+    "direct": dict(pipeline=0, fast_div=0, tile_shift=4),
+}
+
+
+@pytest.fixture(params=list(MODES))
+def mode(request, gpu_lib):
+    """Every kernel configuration must meet the same parity bar."""
+    opts = MODES[request.param]
+    for k, v in opts.items():
+        assert gpu_lib.nb200_set_option(k.encode(), v) >= -1
+    yield request.param
+    for k, v in MODES["pipeline"].items():
+        gpu_lib.nb200_set_option(k.encode(), v)
+
+
 @pytest.mark.parametrize("deck", SMALL_DECKS)
-def test_device_flavour_matches_oracle_every_step(gpu_lib, port, deck):
+def test_device_flavour_matches_oracle_every_step(gpu_lib, port, deck, mode):
     prob = build_problem(deck)
     d = prob.deck
     sim = Simulation(prob)
@@ -50,7 +69,7 @@ def test_device_flavour_matches_oracle_every_step(gpu_lib, port, deck):
 
 
 @pytest.mark.parametrize("deck", SMALL_DECKS)
-def test_device_flavour_matches_golden(gpu_lib, deck):
+def test_device_flavour_matches_golden(gpu_lib, deck, mode):
     g = np.load(os.path.join(GOLDEN, f"{deck}.npz"))
     prob = build_problem(deck)
     sim = Simulation(prob)
