@@ -336,8 +336,10 @@ void run_step(Bank* bank, int nx, int ny, uint64_t master_key, double dt, int nt
   CU_FATAL(cudaMemcpyAsync(g.h_totals, g.d_totals, sizeof(unsigned long long) * kTotCount,
                            cudaMemcpyDeviceToHost, g.stream));
   CU_FATAL(cudaStreamSynchronize(g.stream));
-  if (g.opt_pipeline)  // everything behind the survivors of this step is dead from now on
-    bank->n_upper = (int)(g.h_totals[kTotProcessed] - g.h_totals[kTotDeaths]);
+  // The sort compacted every particle that was dead at the start of this step behind the
+  // live prefix; particles that died DURING the step still sit inside the prefix (the next
+  // sort moves them out), so the prefix to visit next step is this step's live count.
+  if (g.opt_pipeline) bank->n_upper = (int)g.h_totals[kTotProcessed];
 
   for (int k = 0; k < kTotCount; ++k) g.last_stats[k] = g.h_totals[k];
   g.last_stats[5] = g.launches - launches0;
