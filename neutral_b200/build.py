@@ -13,8 +13,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libneutral_b200.so")
-SOURCES = ["transport.cu", "pipeline.cu", "capi.cu"]
+# NB200_LIB / NB200_DEFINES build and load an experiment variant next to the product library
+# (e.g. NB200_DEFINES=-DNB_HISTORY_MIN_BLOCKS=5 NB200_LIB=libneutral_b200.mb5.so).
+LIB = os.path.join(HERE, os.environ.get("NB200_LIB", "libneutral_b200.so"))
+SOURCES = ["transport.cu", "stage.cu", "pipeline.cu", "history.cu", "capi.cu"]
 HEADERS = ["transport.cuh", "nb_device.cuh", "nb_bank.cuh", "nb_math.cuh", "glibc_log_table.inc",
            os.path.join("..", "..", "include", "neutral_b200.h")]
 
@@ -45,7 +47,7 @@ def is_stale() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + ["-shared"] + \
+    cmd = [find_nvcc()] + NVCC_FLAGS + os.environ.get("NB200_DEFINES", "").split() + ["-shared"] + \
         [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB, "-lgomp"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr

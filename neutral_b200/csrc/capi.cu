@@ -48,6 +48,29 @@ struct BankHandle {
   Bank* impl;
 };
 
+constexpr int kCsBuckets = 8192;
+
+// Parameters of the bucket index of one table (CsStage in nb_bank.cuh).
+struct CsParams {
+  unsigned long long bits0 = 0;
+  int shift = 63;
+  int nb = 1;  // one bucket = plain bisection over the whole grid (always valid)
+};
+
+CsParams cs_params_from_host(const double* keys, int n) {
+  CsParams p;
+  if (n >= 2 && keys[0] > 0.0 && keys[n - 1] > keys[0]) {
+    unsigned long long lo, hi;
+    memcpy(&lo, &keys[0], 8);
+    memcpy(&hi, &keys[n - 1], 8);
+    p.bits0 = lo;
+    p.nb = kCsBuckets;
+    p.shift = 0;
+    while (((hi - lo) >> p.shift) >= (unsigned long long)p.nb) p.shift++;
+  }
+  return p;
+}
+
 struct Context {
   bool ready = false;
   int device = 0;
@@ -67,11 +90,19 @@ struct Context {
   int opt_pipeline = 1;
   int shard_first = 0;
   int shard_count = -1;
-  // cross-section grids seen last (same-grid detection is cached per table pair)
+  // cross-section grids seen last: same-grid detection and the bucket-index parameters are
+  // derived from a host copy of the keys once per (pointer, size) pair; the staging kernels
+  // re-verify them on the device every step (kTotFault)
   const double* cs_s_keys = nullptr;
   const double* cs_a_keys = nullptr;
-  int cs_n = 0;
+  int cs_n = 0, cs_a_n = 0;
   int cs_same = 0;
+  CsParams cs_s_par, cs_a_par;
+  // per-step staging (stage.cu): cross-section tables and the density tile map
+  char* d_cs_stage = nullptr;
+  size_t cs_stage_bytes = 0;
+  double* d_tile_rho = nullptr;
+  int tile_capacity = 0;
   std::string last_error;
 };
 
@@ -246,11 +277,12 @@ void upload_host_soa(const SoaView& host, int count, BankView& dst) {
   soa_release(staging);
 }
 
-int detect_same_grid(const double* s_keys, int s_n, const double* a_keys, int a_n) {
-  if (s_n != a_n) return 0;
-  if (s_keys == a_keys) return 1;
-  if (g.cs_s_keys == s_keys && g.cs_a_keys == a_keys && g.cs_n == s_n) return g.cs_same;
-  std::vector<double> hs(s_n), ha(a_n);
+// Looks at the two energy grids once per (pointer, size) pair: are they the same grid, and
+// which leading bits spread their keys over the bucket index.
+int inspect_tables(const double* s_keys, int s_n, const double* a_keys, int a_n) {
+  if (g.cs_s_keys == s_keys && g.cs_a_keys == a_keys && g.cs_n == s_n && g.cs_a_n == a_n)
+    return g.cs_same;
+  std::vector<double> hs(std::max(s_n, 1)), ha(std::max(a_n, 1));
   CU_FATAL(cudaMemcpyAsync(hs.data(), s_keys, sizeof(double) * s_n, cudaMemcpyDeviceToHost,
                            g.stream));
   CU_FATAL(cudaMemcpyAsync(ha.data(), a_keys, sizeof(double) * a_n, cudaMemcpyDeviceToHost,
@@ -259,8 +291,50 @@ int detect_same_grid(const double* s_keys, int s_n, const double* a_keys, int a_
   g.cs_s_keys = s_keys;
   g.cs_a_keys = a_keys;
   g.cs_n = s_n;
-  g.cs_same = memcmp(hs.data(), ha.data(), sizeof(double) * s_n) == 0;
+  g.cs_a_n = a_n;
+  g.cs_same = s_n == a_n && memcmp(hs.data(), ha.data(), sizeof(double) * s_n) == 0;
+  g.cs_s_par = cs_params_from_host(hs.data(), s_n);
+  g.cs_a_par = cs_params_from_host(ha.data(), a_n);
   return g.cs_same;
+}
+
+// Restages both tables into the library's own block (stage.cu) and fills the views.
+void stage_tables(StepArgs& a) {
+  auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t kv_s = align(sizeof(double2) * a.s_n), kv_a = align(sizeof(double2) * a.a_n);
+  const size_t bk_s = align(sizeof(int) * (g.cs_s_par.nb + 1));
+  const size_t bk_a = align(sizeof(int) * (g.cs_a_par.nb + 1));
+  const size_t need = kv_s + kv_a + bk_s + bk_a;
+  if (g.cs_stage_bytes < need) {
+    cudaFree(g.d_cs_stage);
+    CU_FATAL(cudaMalloc(&g.d_cs_stage, need));
+    g.cs_stage_bytes = need;
+  }
+  char* p = g.d_cs_stage;
+  double2* d_kv_s = (double2*)p; p += kv_s;
+  double2* d_kv_a = (double2*)p; p += kv_a;
+  int* d_bk_s = (int*)p; p += bk_s;
+  int* d_bk_a = (int*)p;
+  g.launches += launch_stage_cs(a.s_keys, a.s_vals, a.s_n, d_kv_s, d_bk_s, g.cs_s_par.bits0,
+                                g.cs_s_par.shift, g.cs_s_par.nb,
+                                a.same_keys ? a.a_keys : nullptr, a.totals, g.stream);
+  g.launches += launch_stage_cs(a.a_keys, a.a_vals, a.a_n, d_kv_a, d_bk_a, g.cs_a_par.bits0,
+                                g.cs_a_par.shift, g.cs_a_par.nb, nullptr, a.totals, g.stream);
+  a.cs_s = CsStage{d_kv_s, d_bk_s, g.cs_s_par.bits0, g.cs_s_par.shift, g.cs_s_par.nb, a.s_n};
+  a.cs_a = CsStage{d_kv_a, d_bk_a, g.cs_a_par.bits0, g.cs_a_par.shift, g.cs_a_par.nb, a.a_n};
+}
+
+void stage_tiles(StepArgs& a) {
+  const int tiles_x = ((a.nx - 1) >> kTileShift) + 1;
+  const int ntiles = tiles_x * (((a.ny - 1) >> kTileShift) + 1);
+  if (g.tile_capacity < ntiles) {
+    cudaFree(g.d_tile_rho);
+    CU_FATAL(cudaMalloc(&g.d_tile_rho, sizeof(double) * ntiles));
+    g.tile_capacity = ntiles;
+  }
+  g.launches += launch_stage_tiles(a.density, a.nx, a.ny, tiles_x, ntiles, g.d_tile_rho,
+                                   g.stream);
+  a.tiles = TileMap{g.d_tile_rho, tiles_x};
 }
 
 // The one timestep both flavours share. All pointers are device memory.
@@ -287,7 +361,7 @@ void run_step(Bank* bank, int nx, int ny, uint64_t master_key, double dt, int nt
   a.a_keys = a_keys;
   a.a_vals = a_vals;
   a.a_n = a_n;
-  a.same_keys = detect_same_grid(s_keys, s_n, a_keys, a_n);
+  a.same_keys = inspect_tables(s_keys, s_n, a_keys, a_n);
   a.tally = tally;
   a.p_facets = (unsigned long long*)r0;
   a.p_collisions = (unsigned long long*)r1;
@@ -299,6 +373,9 @@ void run_step(Bank* bank, int nx, int ny, uint64_t master_key, double dt, int nt
   CU_FATAL(cudaMemsetAsync(g.d_totals, 0, sizeof(unsigned long long) * kTotCount, g.stream));
   CU_FATAL(cudaEventRecord(g.ev_begin, g.stream));
   if (g.opt_pipeline) {
+    // P0: restage the read-only inputs (cross-section tables, density tile map)
+    stage_tables(a);
+    stage_tiles(a);
     // P1-P3: begin-step set-up, classification and counting sort into the double buffer
     SortArgs s{};
     s.tile_shift = g.opt_tile_shift;
@@ -336,6 +413,9 @@ void run_step(Bank* bank, int nx, int ny, uint64_t master_key, double dt, int nt
   CU_FATAL(cudaMemcpyAsync(g.h_totals, g.d_totals, sizeof(unsigned long long) * kTotCount,
                            cudaMemcpyDeviceToHost, g.stream));
   CU_FATAL(cudaStreamSynchronize(g.stream));
+  if (g.h_totals[kTotFault])
+    terminate("solve_transport_2d: the cross-section tables are not what they were when first "
+              "seen (energy grid not strictly increasing, or the two grids no longer equal)");
   // The sort compacted every particle that was dead at the start of this step behind the
   // live prefix; particles that died DURING the step still sit inside the prefix (the next
   // sort moves them out), so the prefix to visit next step is this step's live count.
@@ -648,7 +728,7 @@ extern "C" void nb200_solve_transport_2d_host(
   bank.pid0 = 0;
   bank_alloc(bank.cur, n);
   g.launches += launch_import_aos(bank.cur, d_aos, n, g.stream);
-  g.cs_s_keys = nullptr;  // fresh uploads: never trust the cached grid comparison
+  g.cs_s_keys = nullptr;  // fresh uploads: never trust the cached table inspection
   run_step(&bank, nx, ny, master_key, dt, ntotal_particles, d_density, d_edgex, d_edgey, d_sk,
            d_sv, s_n, d_ak, d_av, a_n, d_tally, d_r[0], d_r[1], d_r[2], facet_events,
            collision_events);
@@ -922,11 +1002,22 @@ extern "C" int nb200_selftest_cs(const double* keys_host, const double* values_h
   CU_TRY(cudaMemcpyAsync(d_k, keys_host, sizeof(double) * nentries, cudaMemcpyHostToDevice, g.stream));
   CU_TRY(cudaMemcpyAsync(d_v, values_host, sizeof(double) * nentries, cudaMemcpyHostToDevice, g.stream));
   CU_TRY(cudaMemcpyAsync(d_e, energies_host, sizeof(double) * n, cudaMemcpyHostToDevice, g.stream));
-  g.launches += launch_selftest_cs(d_k, d_v, nentries, d_e, n, d_i, d_o, g.stream);
+  // stage the table exactly as a timestep does, then run both lookups side by side
+  const CsParams par = cs_params_from_host(keys_host, nentries);
+  double2* d_kv = nullptr;
+  int* d_bk = nullptr;
+  CU_TRY(cudaMalloc(&d_kv, sizeof(double2) * nentries));
+  CU_TRY(cudaMalloc(&d_bk, sizeof(int) * (par.nb + 1)));
+  CU_TRY(cudaMemsetAsync(g.d_totals, 0, sizeof(unsigned long long) * kTotCount, g.stream));
+  g.launches += launch_stage_cs(d_k, d_v, nentries, d_kv, d_bk, par.bits0, par.shift, par.nb,
+                                nullptr, g.d_totals, g.stream);
+  const CsStage staged{d_kv, d_bk, par.bits0, par.shift, par.nb, nentries};
+  g.launches += launch_selftest_cs(d_k, d_v, nentries, staged, d_e, n, d_i, d_o, g.stream);
   CU_TRY(cudaMemcpyAsync(index_host, d_i, sizeof(int) * n, cudaMemcpyDeviceToHost, g.stream));
   CU_TRY(cudaMemcpyAsync(value_host, d_o, sizeof(double) * n, cudaMemcpyDeviceToHost, g.stream));
   CU_TRY(cudaStreamSynchronize(g.stream));
   cudaFree(d_k); cudaFree(d_v); cudaFree(d_e); cudaFree(d_o); cudaFree(d_i);
+  cudaFree(d_kv); cudaFree(d_bk);
   return 0;
 }
 

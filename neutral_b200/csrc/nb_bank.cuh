@@ -43,7 +43,38 @@ struct SoaView {
 };
 
 // Step totals, one 64-bit counter each (device memory, zeroed by the host per step).
-enum { kTotFacets = 0, kTotCollisions, kTotProcessed, kTotCensus, kTotDeaths, kTotCount = 8 };
+// kTotFault is raised by the staging kernels when what they find on the device contradicts
+// what the host assumed (see stage.cu); the host turns it into a fatal error.
+enum { kTotFacets = 0, kTotCollisions, kTotProcessed, kTotCensus, kTotDeaths, kTotFault = 7,
+       kTotCount = 8 };
+
+// Staged copy of one reference CrossSection (neutral_data.h:38-43), rebuilt from the caller's
+// device arrays at the start of every timestep (stage.cu):
+//   kv[i]      = {keys[i], values[i]}  - one 16-byte load fetches a grid point
+//   bucket[b]  = number of keys whose bucket id is < b, with
+//                bucket id(E) = clamp((bits(E) - bits0) >> shift, 0, nb - 1)
+// The bracketing interval of an energy in bucket b lies in [bucket[b] - 1, bucket[b + 1]],
+// so the lookup bisects a handful of entries instead of the whole grid. The map is
+// monotone for ANY bits0/shift, so the index is exact whatever the keys are; bits0/shift
+// only decide how evenly the keys spread over the buckets.
+struct CsStage {
+  const double2* kv;
+  const int* bucket;
+  unsigned long long bits0;
+  int shift;
+  int nb;
+  int n;
+};
+
+// Density tile map, rebuilt every timestep (stage.cu): tile_rho[t] holds the density of
+// tile t when all its cells carry the same bit pattern, else the kMixedTile marker (then
+// the cell's own density is loaded). Tiles are (1 << kTileShift)^2 cells.
+constexpr int kTileShift = 4;
+constexpr unsigned long long kMixedTileBits = 0x7ff8b200dead0001ull;  // a NaN payload of ours
+struct TileMap {
+  const double* tile_rho;
+  int tiles_x;
+};
 
 struct StepArgs {
   int nx, ny;  // mesh cells (pad = 0, offsets = 0: the only configuration main.c produces)
@@ -70,6 +101,9 @@ struct StepArgs {
   unsigned long long* totals;
   BankView bank;
   const LogTable* logt;
+  // staged per-step copies (stage.cu); kernels that do not use them ignore the fields
+  CsStage cs_s, cs_a;
+  TileMap tiles;
 };
 
 // Scratch of the per-step counting sort (pipeline.cu).

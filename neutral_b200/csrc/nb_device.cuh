@@ -35,6 +35,70 @@ __device__ __forceinline__ void cs_lookup_pair(const StepArgs& a, double e, doub
   sig_a = cs_interp(a.a_keys, a.a_vals, ia, e);
 }
 
+// --------------------------------------------------------------------------------------
+// The same lookup on the staged tables (CsStage, stage.cu): the bucket index narrows the
+// bisection to the few grid points that share the energy's leading bits. The interval found
+// is the unique bracketing interval, i.e. the reference's `ind` (clamped to the end
+// intervals outside the grid, like the oracle's bisection).
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ int cs_bracket_staged(const CsStage& c, double e) {
+  const long long d = (long long)(double_to_bits(e) - c.bits0);
+  int b = 0;
+  if (d > 0) {
+    const unsigned long long q = (unsigned long long)d >> c.shift;
+    b = q < (unsigned long long)(c.nb - 1) ? (int)q : c.nb - 1;
+  }
+  int lo = max(__ldg(c.bucket + b) - 1, 0);
+  int hi = min(__ldg(c.bucket + b + 1), c.n - 1);
+  lo = min(lo, c.n - 2);
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (e < __ldg(&c.kv[mid].x)) hi = mid; else lo = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ void cs_lookup_pair_staged(const StepArgs& a, double e,
+                                                      double& sig_s, double& sig_a) {
+  const int is = cs_bracket_staged(a.cs_s, e);
+  const double2 s0 = __ldg(a.cs_s.kv + is), s1 = __ldg(a.cs_s.kv + is + 1);
+  const double frac = (e - s0.x) / (s1.x - s0.x);
+  sig_s = s0.y + frac * (s1.y - s0.y);
+  if (a.same_keys) {
+    // identical grids: the interval and the interpolation weight are the same bits
+    const double va0 = __ldg(&a.cs_a.kv[is].y), va1 = __ldg(&a.cs_a.kv[is + 1].y);
+    sig_a = va0 + frac * (va1 - va0);
+  } else {
+    const int ia = cs_bracket_staged(a.cs_a, e);
+    const double2 a0 = __ldg(a.cs_a.kv + ia), a1 = __ldg(a.cs_a.kv + ia + 1);
+    sig_a = a0.y + ((e - a0.x) / (a1.x - a0.x)) * (a1.y - a0.y);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Exact division by a divisor whose correctly rounded reciprocal is known.
+//   q0 = a*y, two FMA refinements; the last one is Markstein's correction step: with
+//   y = RN(1/b) and q1 within one ulp of a/b, RN(q1 + (a - b*q1)*y) == RN(a/b).
+// Guarded to operands far from overflow/underflow; anything else takes the IEEE divide.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ bool safe_exponent(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v) & 0x7ff00000u;
+  return hi - 0x30000000u < 0x20000000u;  // 2^-255 <= |v| < 2^257: quotients stay normal
+}
+
+__device__ __forceinline__ double div_by_known_unchecked(double a, double b, double y) {
+  const double q0 = a * y;
+  const double r0 = fma(-b, q0, a);
+  const double q1 = fma(r0, y, q0);
+  const double r1 = fma(-b, q1, a);
+  return fma(r1, y, q1);
+}
+
+__device__ __forceinline__ double div_by_known(double a, double b, double y) {
+  if (safe_exponent(a) && safe_exponent(b)) return div_by_known_unchecked(a, b, y);
+  return a / b;
+}
+
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

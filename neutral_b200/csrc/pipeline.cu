@@ -11,8 +11,7 @@
 //   P3 k_scatter      stable-enough counting sort of the bank into its double buffer:
 //                     colliders first (longest histories), then streamers by tile, census,
 //                     dead particles compacted to the tail. Warp ballot/match aggregation.
-//   P4 k_history      event loop to census/death on event-type-coherent warps, with every
-//                     quantity that is invariant between events kept in registers.
+//   P4 k_history      (history.cu) event loop to census/death on event-type-coherent warps.
 //
 // Bit-exactness: reordering the bank cannot change a history (RNG streams are keyed by the
 // particle's origin, omp3/neutral.c:89,632-641) and every cached quantity is recomputed with
@@ -22,28 +21,6 @@
 #include "transport.cuh"
 
 namespace nb {
-
-// ------------------------------------------------------------------------------------
-// Exact division by a divisor whose correctly rounded reciprocal is known.
-//   q0 = a*y, two FMA refinements; the last one is Markstein's correction step: with
-//   y = RN(1/b) and q1 within one ulp of a/b, RN(q1 + (a - b*q1)*y) == RN(a/b).
-// Guarded to operands far from overflow/underflow; anything else takes the IEEE divide.
-// ------------------------------------------------------------------------------------
-__device__ __forceinline__ bool safe_exponent(double v) {
-  const unsigned hi = (unsigned)__double2hiint(v) & 0x7ff00000u;
-  return hi - 0x20000000u < 0x40000000u;  // 2^-511 <= |v| < 2^513
-}
-
-__device__ __forceinline__ double div_by_known(double a, double b, double y) {
-  if (safe_exponent(a) && safe_exponent(b)) {
-    const double q0 = a * y;
-    const double r0 = fma(-b, q0, a);
-    const double q1 = fma(r0, y, q0);
-    const double r1 = fma(-b, q1, a);
-    return fma(r1, y, q1);
-  }
-  return a / b;
-}
 
 enum { kClsCollision = 0, kClsFacet = 1, kClsCensus = 2, kNumClasses = 3 };
 
@@ -83,7 +60,7 @@ __global__ void __launch_bounds__(256) k_begin_step(const StepArgs a, const Sort
       const int cx = m.x, cy = m.y;
       const double rho = __ldg(a.density + (size_t)cy * a.nx + cx);
       double sig_s, sig_a;
-      cs_lookup_pair(a, e, sig_s, sig_a);
+      cs_lookup_pair_staged(a, e, sig_s, sig_a);
       const double nd = number_density(rho);
       const double Sig_s = macroscopic(nd, sig_s);
       const double Sig_a = macroscopic(nd, sig_a);
@@ -168,171 +145,6 @@ __global__ void __launch_bounds__(256) k_scatter(const BankView src, const BankV
   }
 }
 
-// ------------------------------------------------------------------------------------
-// P4: the event loop. Starts after k_begin_step (dt_to_census = dt and the first path sample
-// are in the bank, the RNG counter stands at 1).
-// ------------------------------------------------------------------------------------
-template <bool kFastDiv>
-__global__ void __launch_bounds__(kHistoryThreads) k_history(const StepArgs a,
-                                                             const unsigned* __restrict__ n_live) {
-  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long nf = 0, nc = 0, nz = 0, np = 0, ndead = 0;
-
-  int4 m = make_int4(0, 0, 1, 0);
-  if (slot < (int)*n_live) m = a.bank.meta[slot];
-
-  if (!m.z) {
-    np = 1;
-    const uint64_t pkey = a.pid0 + (uint64_t)(unsigned)m.w;
-    const double2 pos = a.bank.pos[slot];
-    const double2 dir = a.bank.dir[slot];
-    const double2 ew = a.bank.ew[slot];
-    const double2 tm = a.bank.tm[slot];
-    double x = pos.x, y = pos.y, ox = dir.x, oy = dir.y, e = ew.x, w = ew.y;
-    double dtc = tm.x, mfp = tm.y;
-    int cx = m.x, cy = m.y;
-    int dead = 0;
-    uint64_t counter = 1;
-    double edep = 0.0;
-
-    // Quantities that only change on a collision (energy) ...
-    double sig_s, sig_a;
-    cs_lookup_pair(a, e, sig_s, sig_a);
-    double sig_t = sig_s + sig_a;
-    double stb = sig_t * kBarns;
-    double heat = heating_response(e, sig_a, sig_t);
-    double v = speed_of(e);
-    double v_inv = kFastDiv ? 1.0 / v : 0.0;
-    double uxi = 1.0 / (ox * v);
-    double uyi = 1.0 / (oy * v);
-    // ... and quantities that only change with the cell's density
-    double rho = __ldg(a.density + (size_t)cy * a.nx + cx);
-    double nd = number_density(rho);
-    double Sig_s = macroscopic(nd, sig_s);
-    double Sig_a = macroscopic(nd, sig_a);
-    double Sig_t = Sig_s + Sig_a;
-    double cell_mfp = 1.0 / Sig_t;
-    double cell_mfp_inv = kFastDiv ? 1.0 / cell_mfp : 0.0;
-
-    while (dtc > 0.0) {
-      // calc_distance_to_facet, omp3/neutral.c:423-471
-      const double gx = (ox >= 0.0) ? (__ldg(a.edgex + cx + 1) - x)
-                                    : ((__ldg(a.edgex + cx) - kOpenBoundCorrection) - x);
-      const double gy = (oy >= 0.0) ? (__ldg(a.edgey + cy + 1) - y)
-                                    : ((__ldg(a.edgey + cy) - kOpenBoundCorrection) - y);
-      const bool x_facet = (gx * uxi) < (gy * uyi);
-      const double d_facet = x_facet ? (gx * v) * uxi : (gy * v) * uyi;
-      const double d_coll = mfp * cell_mfp;  // :144-146
-      const double d_census = v * dtc;
-
-      if (d_coll < d_facet && d_coll < d_census) {
-        // ---- collision_event, :209-300
-        nc++;
-        edep += deposition(w, d_coll, stb, heat, nd);
-        x += d_coll * ox;
-        y += d_coll * oy;
-        const double p_absorb = Sig_a / Sig_t;
-        double a0, a1;
-        random_pair(pkey, a.master_key, counter++, a0, a1);
-        const double v_old = v;
-        const double v_old_inv = v_inv;
-        if (a0 < p_absorb) {
-          w *= (1.0 - p_absorb);
-          if (e < kMinEnergyOfInterest) {
-            dead = 1;
-            ndead = 1;
-            atomicAdd(a.tally + (size_t)cy * a.nx + cx, edep * a.inv_ntotal);
-            edep = 0.0;
-            break;
-          }
-          // Energy and direction are unchanged: the lookups of :285-291 return the values
-          // already held, so nothing that depends on them needs recomputing.
-        } else {
-          const double mu = 1.0 - 2.0 * a1;
-          const double e_new = (e * ((kMassNo * kMassNo + (2.0 * kMassNo) * mu) + 1.0)) /
-                               ((kMassNo + 1.0) * (kMassNo + 1.0));
-          const double ct = 0.5 * ((kMassNo + 1.0) * sqrt(e_new / e) -
-                                   (kMassNo - 1.0) * sqrt(e / e_new));
-          const double st = sqrt(1.0 - ct * ct);
-          const double nox = ox * ct - oy * st;
-          const double noy = ox * st + oy * ct;
-          ox = nox;
-          oy = noy;
-          e = e_new;
-          cs_lookup_pair(a, e, sig_s, sig_a);
-          sig_t = sig_s + sig_a;
-          stb = sig_t * kBarns;
-          heat = heating_response(e, sig_a, sig_t);
-          Sig_s = macroscopic(nd, sig_s);
-          Sig_a = macroscopic(nd, sig_a);
-          Sig_t = Sig_s + Sig_a;
-          cell_mfp = 1.0 / Sig_t;
-          if (kFastDiv) cell_mfp_inv = 1.0 / cell_mfp;
-          v = speed_of(e);
-          if (kFastDiv) v_inv = 1.0 / v;
-          uxi = 1.0 / (ox * v);
-          uyi = 1.0 / (oy * v);
-        }
-        mfp = -nb_log(random_first(pkey, a.master_key, counter++), a.logt) / Sig_s;
-        dtc -= kFastDiv ? div_by_known(d_coll, v_old, v_old_inv) : d_coll / v_old;
-      } else if (d_facet < d_census) {
-        // ---- facet_event, :303-380
-        nf++;
-        mfp -= kFastDiv ? div_by_known(d_facet, cell_mfp, cell_mfp_inv) : d_facet / cell_mfp;
-        dtc -= kFastDiv ? div_by_known(d_facet, v, v_inv) : d_facet / v;
-        edep += deposition(w, d_facet, stb, heat, nd);
-        atomicAdd(a.tally + (size_t)cy * a.nx + cx, edep * a.inv_ntotal);
-        edep = 0.0;
-        x += d_facet * ox;
-        y += d_facet * oy;
-        if (x_facet) {
-          if (ox > 0.0) {
-            if (cx >= a.nx - 1) { ox = -ox; uxi = -uxi; } else cx++;
-          } else if (ox < 0.0) {
-            if (cx <= 0) { ox = -ox; uxi = -uxi; } else cx--;
-          }
-        } else {
-          if (oy > 0.0) {
-            if (cy >= a.ny - 1) { oy = -oy; uyi = -uyi; } else cy++;
-          } else if (oy < 0.0) {
-            if (cy <= 0) { oy = -oy; uyi = -uyi; } else cy--;
-          }
-        }
-        const double rho_new = __ldg(a.density + (size_t)cy * a.nx + cx);
-        if (__double_as_longlong(rho_new) != __double_as_longlong(rho)) {
-          rho = rho_new;
-          nd = number_density(rho);
-          Sig_s = macroscopic(nd, sig_s);
-          Sig_a = macroscopic(nd, sig_a);
-          Sig_t = Sig_s + Sig_a;
-          cell_mfp = 1.0 / Sig_t;
-          if (kFastDiv) cell_mfp_inv = 1.0 / cell_mfp;
-        }
-      } else {
-        // ---- census_event, :383-405
-        nz++;
-        x += d_census * ox;
-        y += d_census * oy;
-        mfp -= d_census / cell_mfp;
-        edep += deposition(w, d_census, stb, heat, nd);
-        atomicAdd(a.tally + (size_t)cy * a.nx + cx, edep * a.inv_ntotal);
-        dtc = 0.0;
-        break;
-      }
-    }
-
-    a.bank.pos[slot] = make_double2(x, y);
-    a.bank.dir[slot] = make_double2(ox, oy);
-    a.bank.ew[slot] = make_double2(e, w);
-    a.bank.tm[slot] = make_double2(dtc, mfp);
-    a.bank.meta[slot] = make_int4(cx, cy, dead, m.w);
-    if (a.p_facets) a.p_facets[m.w] += nf;
-    if (a.p_collisions) a.p_collisions[m.w] += nc;
-    if (a.p_census) a.p_census[m.w] += nz;
-  }
-  flush_totals(a.totals, nf, nc, np, nz, ndead);
-}
-
 // Self-test hook: q[i] = div_by_known(a[i], b[i], 1/b[i]) next to the IEEE quotient.
 __global__ void k_selftest_div(const double* a, const double* b, double* fast, double* ieee,
                                int n) {
@@ -356,17 +168,6 @@ int launch_sort_phase(const StepArgs& a, const SortArgs& s, const BankView& alt,
   k_scan_bins<<<1, 1024, 0, st>>>(s);
   k_scatter<<<blocks_for(s.n, 256), 256, 0, st>>>(a.bank, alt, s);
   return 3;
-}
-
-int launch_history(const StepArgs& a, const unsigned* n_live, int n_upper, bool fast_div,
-                   cudaStream_t st) {
-  if (n_upper <= 0) return 0;
-  const int blocks = blocks_for(n_upper, kHistoryThreads);
-  if (fast_div)
-    k_history<true><<<blocks, kHistoryThreads, 0, st>>>(a, n_live);
-  else
-    k_history<false><<<blocks, kHistoryThreads, 0, st>>>(a, n_live);
-  return 1;
 }
 
 int launch_selftest_div(const double* a, const double* b, double* fast, double* ieee, int n,

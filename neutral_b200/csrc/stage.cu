@@ -1,0 +1,104 @@
+// stage.cu - per-timestep staging of the read-only inputs of the history kernel (sm_100a).
+//
+// The caller hands solve_transport_2d plain device arrays (neutral_interface.h:11-20):
+// two cross-section tables (neutral_data.h:38-43) and the density mesh. Both are re-read
+// millions of times per step in a pattern the raw layout serves badly, so every step starts
+// with two tiny kernels that restage them:
+//
+//   k_stage_cs     {key,value} interleaved grid points + a bucket index over the leading
+//                  bits of the energy (CsStage). Replaces the ~15 dependent probes of the
+//                  reference's search (omp3/neutral.c:506-511) by 1-6 probes of one or two
+//                  cache lines. Also checks what the host assumed about the tables.
+//   k_stage_tiles  one density value per uniform 16x16-cell tile (TileMap): a facet crossing
+//                  (omp3/neutral.c:372-378) reads the 4-byte-per-cell-equivalent map, which
+//                  stays cache resident, instead of a random 32-byte sector of the 128 MB
+//                  density mesh.
+//
+// Restaging every step (a few microseconds) means the caller may change the tables or the
+// density between timesteps, exactly as with the reference. Neither structure changes a
+// result: the bracketing interval of an energy is unique and a uniform tile's value is the
+// cell's own density, bit for bit.
+#include "nb_device.cuh"
+#include "transport.cuh"
+
+namespace nb {
+
+__device__ __forceinline__ int stage_bucket_id(double key, unsigned long long bits0, int shift,
+                                               int nb) {
+  const long long d = (long long)(double_to_bits(key) - bits0);
+  if (d <= 0) return 0;
+  const unsigned long long q = (unsigned long long)d >> shift;
+  return q < (unsigned long long)(nb - 1) ? (int)q : nb - 1;
+}
+
+__global__ void __launch_bounds__(256) k_stage_cs(const double* __restrict__ keys,
+                                                  const double* __restrict__ vals, int n,
+                                                  double2* __restrict__ kv,
+                                                  int* __restrict__ bucket,
+                                                  unsigned long long bits0, int shift, int nb,
+                                                  const double* __restrict__ twin_keys,
+                                                  unsigned long long* totals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double k = keys[i];
+  kv[i] = make_double2(k, vals[i]);
+  const int b_here = stage_bucket_id(k, bits0, shift, nb);
+  int b_prev = -1;
+  bool fault = false;
+  if (i > 0) {
+    const double k_prev = keys[i - 1];
+    b_prev = stage_bucket_id(k_prev, bits0, shift, nb);
+    fault = !(k_prev < k);  // the grid must be strictly increasing (omp3/neutral.c:506-511)
+  }
+  // bucket[b] = number of keys with id < b: keys 0..i-1 have ids <= b_prev.
+  for (int b = b_prev + 1; b <= b_here; ++b) bucket[b] = i;
+  if (i == n - 1)
+    for (int b = b_here + 1; b <= nb; ++b) bucket[b] = n;
+  // The host claimed both tables share one energy grid: verify it where the data lives.
+  if (twin_keys && double_to_bits(twin_keys[i]) != double_to_bits(k)) fault = true;
+  if (fault) atomicAdd(totals + kTotFault, 1ull);
+}
+
+// One warp per tile; lane l covers row l/2, columns 8*(l%2) .. +7 of the 16x16 tile.
+__global__ void __launch_bounds__(256) k_stage_tiles(const double* __restrict__ density, int nx,
+                                                     int ny, int tiles_x, int ntiles,
+                                                     double* __restrict__ tile_rho) {
+  static_assert(kTileShift == 4, "lane mapping below assumes 16x16 tiles");
+  const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (tile >= ntiles) return;
+  const int lane = threadIdx.x & 31;
+  const int cx0 = (tile % tiles_x) << kTileShift;
+  const int cy0 = (tile / tiles_x) << kTileShift;
+  const unsigned long long first = double_to_bits(density[(size_t)cy0 * nx + cx0]);
+  const int cy = cy0 + (lane >> 1);
+  const int cxb = cx0 + ((lane & 1) << 3);
+  bool same = true;
+  if (cy < ny) {
+    const double* row = density + (size_t)cy * nx;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (cxb + c < nx) same = same && (double_to_bits(row[cxb + c]) == first);
+  }
+  same = __all_sync(0xffffffffu, same) && first != kMixedTileBits;
+  if (lane == 0) tile_rho[tile] = bits_to_double(same ? first : kMixedTileBits);
+}
+
+static inline int blocks_for(size_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+int launch_stage_cs(const double* keys, const double* vals, int n, double2* kv, int* bucket,
+                    unsigned long long bits0, int shift, int nb, const double* twin_keys,
+                    unsigned long long* totals, cudaStream_t st) {
+  if (n <= 0) return 0;
+  k_stage_cs<<<blocks_for(n, 256), 256, 0, st>>>(keys, vals, n, kv, bucket, bits0, shift, nb,
+                                                 twin_keys, totals);
+  return 1;
+}
+
+int launch_stage_tiles(const double* density, int nx, int ny, int tiles_x, int ntiles,
+                       double* tile_rho, cudaStream_t st) {
+  k_stage_tiles<<<blocks_for((size_t)ntiles * 32, 256), 256, 0, st>>>(density, nx, ny, tiles_x,
+                                                                      ntiles, tile_rho);
+  return 1;
+}
+
+}  // namespace nb

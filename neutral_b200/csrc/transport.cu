@@ -251,13 +251,20 @@ __global__ void k_selftest_log(const double* x, double* y, int n, const LogTable
   if (i < n) y[i] = nb_log(x[i], logt);
 }
 
+// Both lookups side by side: the staged one (bucket index, what the pipeline uses) must find
+// the interval of the plain bisection; a disagreement is reported as index -1.
 __global__ void k_selftest_cs(const double* keys, const double* vals, int n_entries,
-                              const double* e, int n, int* ind, double* out) {
+                              CsStage staged, const double* e, int n, int* ind, double* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int b = cs_bracket(keys, n_entries, e[i]);
-  ind[i] = b;
-  out[i] = cs_interp(keys, vals, b, e[i]);
+  const int bs = cs_bracket_staged(staged, e[i]);
+  const double2 p0 = staged.kv[bs], p1 = staged.kv[bs + 1];
+  const double v_staged = p0.y + ((e[i] - p0.x) / (p1.x - p0.x)) * (p1.y - p0.y);
+  const double v_plain = cs_interp(keys, vals, b, e[i]);
+  const bool agree = b == bs && double_to_bits(v_staged) == double_to_bits(v_plain);
+  ind[i] = agree ? bs : -1;
+  out[i] = v_staged;
 }
 
 // dst += src over the tally mesh (combining per-step tally deltas of a sharded run).
@@ -330,9 +337,10 @@ int launch_selftest_log(const double* x, double* y, int n, const LogTable* logt,
   return 1;
 }
 
-int launch_selftest_cs(const double* keys, const double* vals, int n_entries, const double* e,
-                       int n, int* ind, double* out, cudaStream_t st) {
-  k_selftest_cs<<<blocks_for(n, 256), 256, 0, st>>>(keys, vals, n_entries, e, n, ind, out);
+int launch_selftest_cs(const double* keys, const double* vals, int n_entries, CsStage staged,
+                       const double* e, int n, int* ind, double* out, cudaStream_t st) {
+  k_selftest_cs<<<blocks_for(n, 256), 256, 0, st>>>(keys, vals, n_entries, staged, e, n, ind,
+                                                    out);
   return 1;
 }
 

@@ -16,6 +16,12 @@ int launch_sort_phase(const StepArgs& a, const SortArgs& s, const BankView& alt,
                       cudaStream_t st);
 int launch_history(const StepArgs& a, const unsigned* n_live, int n_upper, bool fast_div,
                    cudaStream_t st);
+// Per-step staging of the read-only inputs (stage.cu).
+int launch_stage_cs(const double* keys, const double* vals, int n, double2* kv, int* bucket,
+                    unsigned long long bits0, int shift, int nb, const double* twin_keys,
+                    unsigned long long* totals, cudaStream_t st);
+int launch_stage_tiles(const double* density, int nx, int ny, int tiles_x, int ntiles,
+                       double* tile_rho, cudaStream_t st);
 int launch_selftest_div(const double* a, const double* b, double* fast, double* ieee, int n,
                         cudaStream_t st);
 
@@ -31,7 +37,7 @@ int launch_selftest_rng_log(uint64_t pkey0, uint64_t master_key, uint64_t counte
                             double* neglog, cudaStream_t st);
 int launch_selftest_log(const double* x, double* y, int n, const LogTable* logt,
                         cudaStream_t st);
-int launch_selftest_cs(const double* keys, const double* vals, int n_entries, const double* e,
-                       int n, int* ind, double* out, cudaStream_t st);
+int launch_selftest_cs(const double* keys, const double* vals, int n_entries, CsStage staged,
+                       const double* e, int n, int* ind, double* out, cudaStream_t st);
 
 }  // namespace nb
