@@ -325,16 +325,15 @@ void stage_tables(StepArgs& a) {
 }
 
 void stage_tiles(StepArgs& a) {
-  const int tiles_x = ((a.nx - 1) >> kTileShift) + 1;
-  const int ntiles = tiles_x * (((a.ny - 1) >> kTileShift) + 1);
-  if (g.tile_capacity < ntiles) {
+  const int nfine = (((a.nx - 1) >> kTileShift) + 1) * (((a.ny - 1) >> kTileShift) + 1);
+  const int ncoarse = (((a.nx - 1) >> kCoarseShift) + 1) * (((a.ny - 1) >> kCoarseShift) + 1);
+  if (g.tile_capacity < nfine + ncoarse) {
     cudaFree(g.d_tile_rho);
-    CU_FATAL(cudaMalloc(&g.d_tile_rho, sizeof(double) * ntiles));
-    g.tile_capacity = ntiles;
+    CU_FATAL(cudaMalloc(&g.d_tile_rho, sizeof(double) * (nfine + ncoarse)));
+    g.tile_capacity = nfine + ncoarse;
   }
-  g.launches += launch_stage_tiles(a.density, a.nx, a.ny, tiles_x, ntiles, g.d_tile_rho,
-                                   g.stream);
-  a.tiles = TileMap{g.d_tile_rho, tiles_x};
+  g.launches += launch_stage_tiles(a.density, a.nx, a.ny, g.d_tile_rho, g.d_tile_rho + nfine,
+                                   &a.tiles, g.stream);
 }
 
 // The one timestep both flavours share. All pointers are device memory.
@@ -391,12 +390,14 @@ void run_step(Bank* bank, int nx, int ny, uint64_t master_key, double dt, int nt
     }
     if (g.bins_capacity < s.nbins) {
       cudaFree(g.d_bins);
-      CU_FATAL(cudaMalloc(&g.d_bins, sizeof(unsigned) * 2 * (size_t)s.nbins));
+      // histogram, cursors, and one scan partial per 2048 bins
+      CU_FATAL(cudaMalloc(&g.d_bins, sizeof(unsigned) * (2 * (size_t)s.nbins + s.nbins / 2048 + 1)));
       g.bins_capacity = s.nbins;
     }
     s.keys = bank->keys;
     s.bin_count = g.d_bins;
     s.bin_cursor = g.d_bins + s.nbins;
+    s.chunk_sum = g.d_bins + 2 * (size_t)s.nbins;
     s.n_live = g.d_n_live;
     g.launches += launch_sort_phase(a, s, bank->alt, g.stream);
     std::swap(bank->cur, bank->alt);

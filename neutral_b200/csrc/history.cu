@@ -16,7 +16,9 @@
 //    quotient, bit for bit (nb_device.cuh: div_by_known);
 //  * the cell step/reflect logic (:332-368) is computed on the crossed axis only, without
 //    the reference's four-way branch, so a warp does not serialise over directions;
-//  * the density of the entered cell comes from the per-step tile map (stage.cu) unless the
+//  * the two edges a particle is heading for are carried in registers and only the crossed
+//    axis reloads its next edge - issued before the event's arithmetic, consumed after it;
+//  * the density of the entered cell comes from the per-step tile maps (stage.cu) unless the
 //    tile is mixed; cross sections come from the staged tables through the bucket index;
 //  * the tally index cy*nx+cx is carried along instead of being rebuilt.
 //
@@ -35,48 +37,92 @@ __device__ __forceinline__ bool is_mixed_tile(double t) {
   return double_to_bits(t) == kMixedTileBits;
 }
 
-__device__ __forceinline__ double tile_value(const StepArgs& a, int cx, int cy) {
-  return __ldg(a.tiles.tile_rho + (cy >> kTileShift) * a.tiles.tiles_x + (cx >> kTileShift));
+__device__ __forceinline__ double coarse_value(const StepArgs& a, int cx, int cy) {
+  return __ldg(a.tiles.coarse + (cy >> kCoarseShift) * a.tiles.coarse_tx + (cx >> kCoarseShift));
+}
+
+__device__ __forceinline__ double fine_value(const StepArgs& a, int cx, int cy) {
+  return __ldg(a.tiles.fine + (cy >> kTileShift) * a.tiles.fine_tx + (cx >> kTileShift));
 }
 
 // Per-particle flag bits kept in one register.
 enum : unsigned {
-  kFlagSpeedOk = 1u,    // the speed is inside the proven range of div_by_known
-  kFlagCellMfpOk = 2u,  // so is the cell mean free path
-  kFlagMixedTile = 4u,  // the current tile is not uniform: densities come from the mesh
-  kFlagDead = 8u,
+  kFlagSpeedOk = 1u,      // the speed is inside the proven range of div_by_known
+  kFlagCellMfpOk = 2u,    // so is the cell mean free path
+  kFlagDivOk = kFlagSpeedOk | kFlagCellMfpOk,
+  kFlagCoarseMixed = 4u,  // the current 64x64 tile is not uniform: consult the fine map
+  kFlagFineMixed = 8u,    // nor is the current 16x16 tile: densities come from the mesh
+  kFlagPending = 16u,     // collisions deposited energy that no tally flush has taken yet
+  kFlagDead = 32u,
 };
 
-// Everything that follows from the energy and the cell density (omp3/neutral.c:112-117,
-// 135; 231-232; 481-491), grouped so that the facet loop only carries what it reads.
+// What a facet reads of the quantities that follow from the energy and the cell density
+// (omp3/neutral.c:112-117, 135, 481-491).
 struct Derived {
   double stb;           // (sigma_s + sigma_a) * BARNS, the deposition's cross section
   double heat;          // heating response of :481-491
-  double Sig_s;         // macroscopic scattering cross section (mean-free-path sampling)
-  double p_absorb;      // Sigma_a / Sigma_t, :231-232
   double cell_mfp;      // 1 / Sigma_t, :135
   double cell_mfp_inv;  // correctly rounded 1 / cell_mfp for div_by_known
 };
 
+// Recomputes them - and Sigma_s (mean-free-path sampling, :130,295) and p_absorb (:231-232),
+// which only collisions read - from the energy and the number density.
 __device__ __forceinline__ void derive(const StepArgs& a, double e, double nd, Derived& d,
-                                       unsigned& flags) {
+                                       double& Sig_s, double& p_absorb, unsigned& flags) {
   double sig_s, sig_a;
   cs_lookup_pair_staged(a, e, sig_s, sig_a);
   const double sig_t = sig_s + sig_a;
   d.stb = sig_t * kBarns;
   d.heat = heating_response(e, sig_a, sig_t);
-  d.Sig_s = macroscopic(nd, sig_s);
-  const double Sig_a = macroscopic(nd, sig_a);
-  const double Sig_t = d.Sig_s + Sig_a;
-  d.p_absorb = Sig_a / Sig_t;
-  d.cell_mfp = 1.0 / Sig_t;
+  const double S_s = macroscopic(nd, sig_s);
+  const double S_a = macroscopic(nd, sig_a);
+  const double S_t = S_s + S_a;
+  Sig_s = S_s;
+  p_absorb = S_a / S_t;
+  d.cell_mfp = 1.0 / S_t;
   d.cell_mfp_inv = 1.0 / d.cell_mfp;
   flags = safe_exponent(d.cell_mfp) ? (flags | kFlagCellMfpOk) : (flags & ~kFlagCellMfpOk);
 }
 
+// Direction of travel along one axis as a cell step: +1, -1, or 0 for a component that is
+// exactly zero (omp3/neutral.c:333-366 tests > 0 and < 0 separately).
+__device__ __forceinline__ int axis_step(double o) { return (o > 0.0) ? 1 : ((o < 0.0) ? -1 : 0); }
+
+// The edge a particle in cell c is heading for (omp3/neutral.c:442-444, 448-450): the far
+// edge when the direction component is >= 0, else the near edge pulled in by
+// OPEN_BOUND_CORRECTION.
+__device__ __forceinline__ double target_edge(const double* __restrict__ edge, int c, int step) {
+  const double v = __ldg(edge + c + (step >= 0 ? 1 : 0));
+  return step >= 0 ? v : v - kOpenBoundCorrection;
+}
+
+// State that only collisions (and the rare density change) touch is parked in shared memory,
+// one slot per thread, so that the facet loop's registers hold only what a facet reads:
+// energy, Sigma_s and p_absorb, the density of the cell, and the energy deposited by
+// collisions since the last tally flush (omp3/neutral.c:222-225 accumulates it across
+// consecutive collisions; kFlagPending says the slot is non-zero).
+// -DNB_PARK_SMEM=0 keeps them in registers instead (for A/B measurements).
+#ifndef NB_PARK_SMEM
+#define NB_PARK_SMEM 1
+#endif
+struct Parked {
+  double e[kHistoryThreads];
+  double Sig_s[kHistoryThreads];
+  double p_absorb[kHistoryThreads];
+  double rho[kHistoryThreads];
+  double edep[kHistoryThreads];
+};
+
 template <bool kFastDiv>
 __global__ void __launch_bounds__(kHistoryThreads, NB_HISTORY_MIN_BLOCKS)
 k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
+#if NB_PARK_SMEM
+  __shared__ Parked park;
+#define PARKED(name) park.name[threadIdx.x]
+#else
+  double park_e, park_Sig_s, park_p_absorb, park_rho, park_edep;
+#define PARKED(name) park_##name
+#endif
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned nf = 0, nc = 0, census = 0, processed = 0, died = 0;
 
@@ -89,36 +135,47 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
     const double2 dir = a.bank.dir[slot];
     const double2 ew = a.bank.ew[slot];
     const double2 tm = a.bank.tm[slot];  // k_begin_step left (dt, first path sample) here
-    double x = pos.x, y = pos.y, ox = dir.x, oy = dir.y, e = ew.x, w = ew.y;
+    double x = pos.x, y = pos.y, ox = dir.x, oy = dir.y, w = ew.y;
     double dtc = tm.x, mfp = tm.y;
     int cx = m.x, cy = m.y;
-    unsigned counter = 1;  // counter 0 was drawn by k_begin_step (omp3/neutral.c:129)
+    int cell = cy * a.nx + cx;  // tally / density index, carried along
     unsigned flags = 0;
-    double edep = 0.0;
+    PARKED(e) = ew.x;
+    PARKED(edep) = 0.0;
+    // RNG counter: k_begin_step drew counter 0 (omp3/neutral.c:129); collision number k of
+    // this step draws counters 2k-1 and 2k (:235, :294), so the collision count nc is the
+    // counter state.
 
     // ---- the density of the cell (changes on tile crossings only) ...
-    double rho = tile_value(a, cx, cy);
-    if (is_mixed_tile(rho)) {
-      flags |= kFlagMixedTile;
-      rho = __ldg(a.density + cy * a.nx + cx);
+    double nd;
+    {
+      double rho = coarse_value(a, cx, cy);
+      if (is_mixed_tile(rho)) {
+        flags |= kFlagCoarseMixed;
+        rho = fine_value(a, cx, cy);
+        if (is_mixed_tile(rho)) {
+          flags |= kFlagFineMixed;
+          rho = __ldg(a.density + cell);
+        }
+      }
+      PARKED(rho) = rho;
+      nd = number_density(rho);
     }
-    double nd = number_density(rho);
-    // ---- ... and what follows from the energy (changes on collisions only)
+    // ---- ... what follows from the energy (changes on collisions only) ...
     Derived d;
-    derive(a, e, nd, d, flags);
-    double v = speed_of(e);
+    derive(a, ew.x, nd, d, PARKED(Sig_s), PARKED(p_absorb), flags);
+    double v = speed_of(ew.x);
     double v_inv = 1.0 / v;
     if (safe_exponent(v)) flags |= kFlagSpeedOk;
     double uxi = 1.0 / (ox * v);
     double uyi = 1.0 / (oy * v);
+    // ---- ... and the edges the particle is heading for (change when it crosses or turns)
+    int sx = axis_step(ox), sy = axis_step(oy);
+    double ex = target_edge(a.edgex, cx, sx);
+    double ey = target_edge(a.edgey, cy, sy);
 
     while (dtc > 0.0) {
       // calc_distance_to_facet, omp3/neutral.c:423-471
-      const bool xup = ox >= 0.0, yup = oy >= 0.0;
-      double ex = __ldg(a.edgex + cx + (xup ? 1 : 0));
-      double ey = __ldg(a.edgey + cy + (yup ? 1 : 0));
-      if (!xup) ex -= kOpenBoundCorrection;
-      if (!yup) ey -= kOpenBoundCorrection;
       const double gx = ex - x;
       const double gy = ey - y;
       const bool x_facet = (gx * uxi) < (gy * uyi);
@@ -129,10 +186,17 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
 
       if (!collide && d_facet < d_census) {
         // ---- facet_event, :303-380
+        // :332-368 on the crossed axis only: step one cell, or reflect at the mesh boundary.
+        // Decided first so that the next target edge is in flight during the arithmetic.
+        const int c = x_facet ? cx : cy;
+        const int s = x_facet ? sx : sy;
+        const int cn = c + s;
+        const bool reflect = (unsigned)cn >= (unsigned)(x_facet ? a.nx : a.ny);
+        const double e_next = target_edge(x_facet ? a.edgex : a.edgey, reflect ? c : cn,
+                                          reflect ? -s : s);
         nf++;
         double q_mfp, q_dtc;
-        if (kFastDiv && (flags & (kFlagSpeedOk | kFlagCellMfpOk)) ==
-                            (kFlagSpeedOk | kFlagCellMfpOk) && safe_exponent(d_facet)) {
+        if (kFastDiv && (flags & kFlagDivOk) == kFlagDivOk && safe_exponent(d_facet)) {
           q_mfp = div_by_known_unchecked(d_facet, d.cell_mfp, d.cell_mfp_inv);
           q_dtc = div_by_known_unchecked(d_facet, v, v_inv);
         } else {
@@ -141,56 +205,77 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
         }
         mfp -= q_mfp;
         dtc -= q_dtc;
-        edep += deposition(w, d_facet, d.stb, d.heat, nd);
-        atomicAdd(a.tally + cy * a.nx + cx, edep * a.inv_ntotal);  // update_tallies, :408-420
-        edep = 0.0;
+        // :321-327 - deposit, flush to the tally (update_tallies, :408-420), reset
+        double edep = deposition(w, d_facet, d.stb, d.heat, nd);
+        if (flags & kFlagPending) {
+          edep = PARKED(edep) + edep;
+          PARKED(edep) = 0.0;
+          flags &= ~kFlagPending;
+        }
+        atomicAdd(a.tally + cell, edep * a.inv_ntotal);
         x += d_facet * ox;
         y += d_facet * oy;
-        // :332-368 on the crossed axis: step one cell, or reflect at the mesh boundary
-        const double o = x_facet ? ox : oy;
-        const int c = x_facet ? cx : cy;
-        const int step = (o > 0.0) ? 1 : ((o < 0.0) ? -1 : 0);
-        const int cn = c + step;
-        if ((unsigned)cn >= (unsigned)(x_facet ? a.nx : a.ny)) {
-          if (x_facet) { ox = -ox; uxi = -uxi; } else { oy = -oy; uyi = -uyi; }
+        if (x_facet) ex = e_next; else ey = e_next;
+        if (reflect) {
+          if (x_facet) { ox = -ox; uxi = -uxi; sx = -sx; } else { oy = -oy; uyi = -uyi; sy = -sy; }
         } else {
-          if (x_facet) cx = cn; else cy = cn;
+          if (x_facet) { cx = cn; cell += s; } else { cy = cn; cell += s * a.nx; }
           // :372-378 - the macroscopic cross sections follow the density of the new cell.
-          // Inside a uniform tile the density cannot change; a new tile is looked up in the
-          // tile map; only mixed tiles read the density mesh itself.
-          double rho_new = rho;
-          if ((cn ^ c) >> kTileShift) {
-            rho_new = tile_value(a, cx, cy);
-            flags = is_mixed_tile(rho_new) ? (flags | kFlagMixedTile) : (flags & ~kFlagMixedTile);
-          }
-          if (flags & kFlagMixedTile) rho_new = __ldg(a.density + cy * a.nx + cx);
-          if (double_to_bits(rho_new) != double_to_bits(rho)) {
-            rho = rho_new;
-            nd = number_density(rho);
-            derive(a, e, nd, d, flags);
+          // Inside a uniform coarse tile the density cannot change; otherwise the coarse map,
+          // the fine map and finally the mesh itself are consulted.
+          const int crossed = cn ^ c;
+          if ((crossed >> kCoarseShift) ||
+              (flags & kFlagFineMixed) ||
+              ((flags & kFlagCoarseMixed) && (crossed >> kTileShift))) {
+            double rho_new = PARKED(rho);
+            if (crossed >> kCoarseShift) {
+              const double t = coarse_value(a, cx, cy);
+              if (is_mixed_tile(t)) {
+                flags |= kFlagCoarseMixed;
+              } else {
+                flags &= ~(kFlagCoarseMixed | kFlagFineMixed);
+                rho_new = t;
+              }
+            }
+            if ((flags & kFlagCoarseMixed) && (crossed >> kTileShift)) {
+              const double t = fine_value(a, cx, cy);
+              if (is_mixed_tile(t)) {
+                flags |= kFlagFineMixed;
+              } else {
+                flags &= ~kFlagFineMixed;
+                rho_new = t;
+              }
+            }
+            if (flags & kFlagFineMixed) rho_new = __ldg(a.density + cell);
+            if (double_to_bits(rho_new) != double_to_bits(PARKED(rho))) {
+              PARKED(rho) = rho_new;
+              nd = number_density(rho_new);
+              derive(a, PARKED(e), nd, d, PARKED(Sig_s), PARKED(p_absorb), flags);
+            }
           }
         }
       } else if (collide) {
         // ---- collision_event, :209-300
         nc++;
         const uint64_t pkey = a.pid0 + (uint64_t)(unsigned)m.w;
-        edep += deposition(w, d_coll, d.stb, d.heat, nd);
+        const double e = PARKED(e);
+        const double p_absorb = PARKED(p_absorb);
+        const double edep = PARKED(edep) + deposition(w, d_coll, d.stb, d.heat, nd);  // :222-225
         x += d_coll * ox;
         y += d_coll * oy;
         double a0, a1;
-        random_pair(pkey, a.master_key, counter++, a0, a1);
+        random_pair(pkey, a.master_key, 2ull * nc - 1ull, a0, a1);
         // :296 - the time to census shrinks by the flight time at the pre-collision speed
         double q_dtc;
         if (kFastDiv && (flags & kFlagSpeedOk) && safe_exponent(d_coll))
           q_dtc = div_by_known_unchecked(d_coll, v, v_inv);
         else
           q_dtc = d_coll / v;
-        if (a0 < d.p_absorb) {
-          w *= (1.0 - d.p_absorb);
-          if (e < kMinEnergyOfInterest) {
+        if (a0 < p_absorb) {
+          w *= (1.0 - p_absorb);
+          if (e < kMinEnergyOfInterest) {  // :243-252 - the history ends here
             flags |= kFlagDead;
-            atomicAdd(a.tally + cy * a.nx + cx, edep * a.inv_ntotal);
-            edep = 0.0;
+            atomicAdd(a.tally + cell, edep * a.inv_ntotal);
             break;
           }
           // Energy and direction are unchanged: the lookups of :285-291 return the values
@@ -206,15 +291,21 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
           const double noy = ox * st + oy * ct;
           ox = nox;
           oy = noy;
-          e = e_new;
-          derive(a, e, nd, d, flags);
-          v = speed_of(e);
+          PARKED(e) = e_new;
+          derive(a, e_new, nd, d, PARKED(Sig_s), PARKED(p_absorb), flags);
+          v = speed_of(e_new);
           v_inv = 1.0 / v;
           flags = safe_exponent(v) ? (flags | kFlagSpeedOk) : (flags & ~kFlagSpeedOk);
           uxi = 1.0 / (ox * v);
           uyi = 1.0 / (oy * v);
+          sx = axis_step(ox);
+          sy = axis_step(oy);
+          ex = target_edge(a.edgex, cx, sx);
+          ey = target_edge(a.edgey, cy, sy);
         }
-        mfp = -nb_log(random_first(pkey, a.master_key, counter++), a.logt) / d.Sig_s;
+        PARKED(edep) = edep;
+        flags |= kFlagPending;
+        mfp = -nb_log(random_first(pkey, a.master_key, 2ull * nc), a.logt) / PARKED(Sig_s);
         dtc -= q_dtc;
       } else {
         // ---- census_event, :383-405
@@ -222,8 +313,9 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
         x += d_census * ox;
         y += d_census * oy;
         mfp -= d_census / d.cell_mfp;
-        edep += deposition(w, d_census, d.stb, d.heat, nd);
-        atomicAdd(a.tally + cy * a.nx + cx, edep * a.inv_ntotal);
+        double edep = deposition(w, d_census, d.stb, d.heat, nd);
+        if (flags & kFlagPending) edep = PARKED(edep) + edep;
+        atomicAdd(a.tally + cell, edep * a.inv_ntotal);
         dtc = 0.0;
         break;
       }
@@ -232,7 +324,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
     died = (flags & kFlagDead) ? 1u : 0u;
     a.bank.pos[slot] = make_double2(x, y);
     a.bank.dir[slot] = make_double2(ox, oy);
-    a.bank.ew[slot] = make_double2(e, w);
+    a.bank.ew[slot] = make_double2(PARKED(e), w);
     a.bank.tm[slot] = make_double2(dtc, mfp);
     a.bank.meta[slot] = make_int4(cx, cy, (int)died, m.w);
     if (a.p_facets) a.p_facets[m.w] += nf;
@@ -240,6 +332,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
     if (a.p_census) a.p_census[m.w] += census;
   }
   flush_totals(a.totals, nf, nc, processed, census, died);
+#undef PARKED
 }
 
 static inline int blocks_for(int n, int threads) { return (n + threads - 1) / threads; }

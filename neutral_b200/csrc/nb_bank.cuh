@@ -66,14 +66,20 @@ struct CsStage {
   int n;
 };
 
-// Density tile map, rebuilt every timestep (stage.cu): tile_rho[t] holds the density of
-// tile t when all its cells carry the same bit pattern, else the kMixedTile marker (then
-// the cell's own density is loaded). Tiles are (1 << kTileShift)^2 cells.
+// Density tile maps, rebuilt every timestep (stage.cu). fine[t] holds the density of the
+// 16x16-cell tile t when all its cells carry the same bit pattern, else the kMixedTileBits
+// marker; coarse[] is the same over 64x64-cell tiles (uniform iff its fine tiles are uniform
+// and equal). A facet crossing inside a uniform coarse tile needs no memory access at all;
+// the 31 KB coarse map stays L1-resident, the fine map L2-resident, and only mixed fine
+// tiles read the density mesh itself.
 constexpr int kTileShift = 4;
+constexpr int kCoarseShift = 6;
 constexpr unsigned long long kMixedTileBits = 0x7ff8b200dead0001ull;  // a NaN payload of ours
 struct TileMap {
-  const double* tile_rho;
-  int tiles_x;
+  const double* fine;
+  const double* coarse;
+  int fine_tx;    // fine tiles per mesh row
+  int coarse_tx;  // coarse tiles per mesh row
 };
 
 struct StepArgs {
@@ -111,6 +117,7 @@ struct SortArgs {
   unsigned* keys;        // [n] sort key of every slot in [0, n_upper)
   unsigned* bin_count;   // [nbins] histogram
   unsigned* bin_cursor;  // [nbins] running destination of every bin
+  unsigned* chunk_sum;   // [ceil(nbins / 2048)] scratch of the histogram scan
   unsigned* n_live;      // device scalar: slots in front of the dead bin after the sort
   int nbins;             // 3 classes x ntiles + 1 dead bin
   int ntiles;

@@ -95,32 +95,88 @@ __global__ void __launch_bounds__(256) k_begin_step(const StepArgs a, const Sort
 }
 
 // ------------------------------------------------------------------------------------
-// P2: exclusive scan of the histogram (one CTA; the histogram has at most ~1e6 bins).
-// bin_cursor[b] = first destination slot of bin b; *n_live = start of the dead bin.
+// P2: exclusive scan of the histogram -> bin_cursor[b] = first destination slot of bin b;
+// *n_live = start of the dead bin. Three small launches (the histogram has up to ~2e5 bins):
+// per-chunk sums, scan of the chunk sums by one CTA, per-chunk scan plus chunk offset.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_scan_bins(SortArgs s) {
-  __shared__ unsigned part[1024];
-  const int t = threadIdx.x;
-  const int per = (s.nbins + 1023) / 1024;
-  const int b0 = t * per;
-  const int b1 = min(b0 + per, s.nbins);
-  unsigned sum = 0;
-  for (int b = b0; b < b1; ++b) sum += s.bin_count[b];
-  part[t] = sum;
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanChunk = kScanThreads * kScanItems;  // bins per CTA
+
+// Exclusive scan of one value per thread across the CTA; *total receives the CTA sum.
+__device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* total) {
+  __shared__ unsigned warp_sums[32];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (unsigned)o) inc += t;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
   __syncthreads();
-  // Hillis-Steele inclusive scan over the 1024 partials
-  for (int off = 1; off < 1024; off <<= 1) {
-    const unsigned v = (t >= off) ? part[t - off] : 0u;
+  if (warp == 0) {
+    unsigned w = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= (unsigned)o) w += t;
+    }
+    warp_sums[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  const unsigned before = warp ? warp_sums[warp - 1] : 0u;
+  *total = warp_sums[(blockDim.x >> 5) - 1];
+  return before + inc - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_chunk_sums(SortArgs s, unsigned* chunk_sum) {
+  const int base = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+  unsigned sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k)
+    if (base + k < s.nbins) sum += s.bin_count[base + k];
+  unsigned total;
+  block_exclusive_scan(sum, &total);
+  if (threadIdx.x == 0) chunk_sum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_chunk_offsets(unsigned* chunk_sum, int nchunks) {
+  // nchunks <= 1024 * 8 covers 1.6e7 bins; one value per thread, looped for generality
+  __shared__ unsigned carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nchunks; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const unsigned v = i < nchunks ? chunk_sum[i] : 0u;
+    unsigned total;
+    const unsigned ex = block_exclusive_scan(v, &total);
+    const unsigned c = carry;
+    if (i < nchunks) chunk_sum[i] = c + ex;
     __syncthreads();
-    part[t] += v;
+    if (threadIdx.x == 0) carry = c + total;
     __syncthreads();
   }
-  unsigned run = part[t] - sum;
-  for (int b = b0; b < b1; ++b) {
-    const unsigned c = s.bin_count[b];
-    s.bin_cursor[b] = run;
-    if (b == s.nbins - 1) *s.n_live = run;
-    run += c;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_bins(SortArgs s, const unsigned* chunk_sum) {
+  const int base = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+  unsigned c[kScanItems];
+  unsigned sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    c[k] = base + k < s.nbins ? s.bin_count[base + k] : 0u;
+    sum += c[k];
+  }
+  unsigned total;
+  unsigned run = chunk_sum[blockIdx.x] + block_exclusive_scan(sum, &total);
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (base + k < s.nbins) {
+      s.bin_cursor[base + k] = run;
+      if (base + k == s.nbins - 1) *s.n_live = run;
+    }
+    run += c[k];
   }
 }
 
@@ -165,9 +221,12 @@ int launch_sort_phase(const StepArgs& a, const SortArgs& s, const BankView& alt,
   if (s.n_upper <= 0) return 0;
   cudaMemsetAsync(s.bin_count, 0, sizeof(unsigned) * s.nbins, st);
   k_begin_step<<<blocks_for(s.n_upper, 256), 256, 0, st>>>(a, s);
-  k_scan_bins<<<1, 1024, 0, st>>>(s);
+  const int nchunks = blocks_for(s.nbins, kScanChunk);
+  k_scan_chunk_sums<<<nchunks, kScanThreads, 0, st>>>(s, s.chunk_sum);
+  k_scan_chunk_offsets<<<1, 1024, 0, st>>>(s.chunk_sum, nchunks);
+  k_scan_bins<<<nchunks, kScanThreads, 0, st>>>(s, s.chunk_sum);
   k_scatter<<<blocks_for(s.n, 256), 256, 0, st>>>(a.bank, alt, s);
-  return 3;
+  return 5;
 }
 
 int launch_selftest_div(const double* a, const double* b, double* fast, double* ieee, int n,

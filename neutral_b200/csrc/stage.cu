@@ -9,10 +9,10 @@
 //                  bits of the energy (CsStage). Replaces the ~15 dependent probes of the
 //                  reference's search (omp3/neutral.c:506-511) by 1-6 probes of one or two
 //                  cache lines. Also checks what the host assumed about the tables.
-//   k_stage_tiles  one density value per uniform 16x16-cell tile (TileMap): a facet crossing
-//                  (omp3/neutral.c:372-378) reads the 4-byte-per-cell-equivalent map, which
-//                  stays cache resident, instead of a random 32-byte sector of the 128 MB
-//                  density mesh.
+//   k_stage_tiles  one density value per uniform 16x16-cell tile and, from those
+//   k_stage_coarse (k_stage_coarse), per uniform 64x64-cell tile (TileMap): a facet crossing
+//                  (omp3/neutral.c:372-378) consults the cache-resident maps instead of a
+//                  random 32-byte sector of the 128 MB density mesh.
 //
 // Restaging every step (a few microseconds) means the caller may change the tables or the
 // density between timesteps, exactly as with the reference. Neither structure changes a
@@ -31,6 +31,8 @@ __device__ __forceinline__ int stage_bucket_id(double key, unsigned long long bi
   return q < (unsigned long long)(nb - 1) ? (int)q : nb - 1;
 }
 
+// Threads [0, n) interleave the grid points and check them; threads [0, nb] each find one
+// entry of the bucket index by bisection (bucket[b] = number of keys with id < b).
 __global__ void __launch_bounds__(256) k_stage_cs(const double* __restrict__ keys,
                                                   const double* __restrict__ vals, int n,
                                                   double2* __restrict__ kv,
@@ -39,30 +41,30 @@ __global__ void __launch_bounds__(256) k_stage_cs(const double* __restrict__ key
                                                   const double* __restrict__ twin_keys,
                                                   unsigned long long* totals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double k = keys[i];
-  kv[i] = make_double2(k, vals[i]);
-  const int b_here = stage_bucket_id(k, bits0, shift, nb);
-  int b_prev = -1;
-  bool fault = false;
-  if (i > 0) {
-    const double k_prev = keys[i - 1];
-    b_prev = stage_bucket_id(k_prev, bits0, shift, nb);
-    fault = !(k_prev < k);  // the grid must be strictly increasing (omp3/neutral.c:506-511)
+  if (i < n) {
+    const double k = keys[i];
+    kv[i] = make_double2(k, vals[i]);
+    // the grid must be strictly increasing (the reference's search assumes it,
+    // omp3/neutral.c:506-511) ...
+    bool fault = i > 0 && !(keys[i - 1] < k);
+    // ... and the host claimed both tables share one energy grid: verify it where the data is
+    if (twin_keys && double_to_bits(twin_keys[i]) != double_to_bits(k)) fault = true;
+    if (fault) atomicAdd(totals + kTotFault, 1ull);
   }
-  // bucket[b] = number of keys with id < b: keys 0..i-1 have ids <= b_prev.
-  for (int b = b_prev + 1; b <= b_here; ++b) bucket[b] = i;
-  if (i == n - 1)
-    for (int b = b_here + 1; b <= nb; ++b) bucket[b] = n;
-  // The host claimed both tables share one energy grid: verify it where the data lives.
-  if (twin_keys && double_to_bits(twin_keys[i]) != double_to_bits(k)) fault = true;
-  if (fault) atomicAdd(totals + kTotFault, 1ull);
+  if (i <= nb) {
+    int lo = 0, hi = n;  // first index whose bucket id is >= i
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (stage_bucket_id(keys[mid], bits0, shift, nb) < i) lo = mid + 1; else hi = mid;
+    }
+    bucket[i] = lo;
+  }
 }
 
-// One warp per tile; lane l covers row l/2, columns 8*(l%2) .. +7 of the 16x16 tile.
+// One warp per fine tile; lane l covers row l/2, columns 8*(l%2) .. +7 of the 16x16 tile.
 __global__ void __launch_bounds__(256) k_stage_tiles(const double* __restrict__ density, int nx,
                                                      int ny, int tiles_x, int ntiles,
-                                                     double* __restrict__ tile_rho) {
+                                                     double* __restrict__ fine) {
   static_assert(kTileShift == 4, "lane mapping below assumes 16x16 tiles");
   const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (tile >= ntiles) return;
@@ -80,7 +82,24 @@ __global__ void __launch_bounds__(256) k_stage_tiles(const double* __restrict__ 
       if (cxb + c < nx) same = same && (double_to_bits(row[cxb + c]) == first);
   }
   same = __all_sync(0xffffffffu, same) && first != kMixedTileBits;
-  if (lane == 0) tile_rho[tile] = bits_to_double(same ? first : kMixedTileBits);
+  if (lane == 0) fine[tile] = bits_to_double(same ? first : kMixedTileBits);
+}
+
+// One thread per coarse tile: uniform iff its (up to) 4x4 fine tiles are uniform and equal.
+__global__ void __launch_bounds__(256) k_stage_coarse(const double* __restrict__ fine,
+                                                      int fine_tx, int fine_ty, int coarse_tx,
+                                                      int ncoarse, double* __restrict__ coarse) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncoarse) return;
+  constexpr int kRatio = 1 << (kCoarseShift - kTileShift);
+  const int fx0 = (t % coarse_tx) * kRatio, fy0 = (t / coarse_tx) * kRatio;
+  const unsigned long long first = double_to_bits(fine[fy0 * fine_tx + fx0]);
+  bool same = first != kMixedTileBits;
+  for (int j = 0; j < kRatio; ++j)
+    for (int i = 0; i < kRatio; ++i)
+      if (fy0 + j < fine_ty && fx0 + i < fine_tx)
+        same = same && double_to_bits(fine[(fy0 + j) * fine_tx + fx0 + i]) == first;
+  coarse[t] = bits_to_double(same ? first : kMixedTileBits);
 }
 
 static inline int blocks_for(size_t n, int threads) { return (int)((n + threads - 1) / threads); }
@@ -89,16 +108,21 @@ int launch_stage_cs(const double* keys, const double* vals, int n, double2* kv, 
                     unsigned long long bits0, int shift, int nb, const double* twin_keys,
                     unsigned long long* totals, cudaStream_t st) {
   if (n <= 0) return 0;
-  k_stage_cs<<<blocks_for(n, 256), 256, 0, st>>>(keys, vals, n, kv, bucket, bits0, shift, nb,
+  k_stage_cs<<<blocks_for((size_t)(n > nb + 1 ? n : nb + 1), 256), 256, 0, st>>>(keys, vals, n, kv, bucket, bits0, shift, nb,
                                                  twin_keys, totals);
   return 1;
 }
 
-int launch_stage_tiles(const double* density, int nx, int ny, int tiles_x, int ntiles,
-                       double* tile_rho, cudaStream_t st) {
-  k_stage_tiles<<<blocks_for((size_t)ntiles * 32, 256), 256, 0, st>>>(density, nx, ny, tiles_x,
-                                                                      ntiles, tile_rho);
-  return 1;
+int launch_stage_tiles(const double* density, int nx, int ny, double* fine, double* coarse,
+                       TileMap* map, cudaStream_t st) {
+  const int fine_tx = ((nx - 1) >> kTileShift) + 1, fine_ty = ((ny - 1) >> kTileShift) + 1;
+  const int coarse_tx = ((nx - 1) >> kCoarseShift) + 1, coarse_ty = ((ny - 1) >> kCoarseShift) + 1;
+  k_stage_tiles<<<blocks_for((size_t)fine_tx * fine_ty * 32, 256), 256, 0, st>>>(
+      density, nx, ny, fine_tx, fine_tx * fine_ty, fine);
+  k_stage_coarse<<<blocks_for((size_t)coarse_tx * coarse_ty, 256), 256, 0, st>>>(
+      fine, fine_tx, fine_ty, coarse_tx, coarse_tx * coarse_ty, coarse);
+  *map = TileMap{fine, coarse, fine_tx, coarse_tx};
+  return 2;
 }
 
 }  // namespace nb
