@@ -188,7 +188,8 @@ int nb200_accumulate(double* dst_device, const double* src_device, size_t n);
  * phased timestep - begin-step/classify, counting sort by next-event type and tile, event
  * loop; 0: the direct one-thread-per-history kernel on the unsorted bank); "fast_div"
  * (1, default: exact division by loop-invariant divisors through their reciprocals);
- * "tile_shift" (log2 of the sort tile edge in cells, default 4; < 0: sort by class only).
+ * "tile_shift" (log2 of the sort tile edge in cells, default 9; < 0: no spatial key);
+ * "length_bins" (bins of expected history length in the sort key, default 512; <= 1: none).
  * Returns the previous value, or a negative code for an unknown name. */
 int nb200_set_option(const char* name, int value);
 

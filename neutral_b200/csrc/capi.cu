@@ -83,7 +83,12 @@ struct Context {
   unsigned* d_n_live = nullptr;
   int bins_capacity = 0;
   int opt_fast_div = 1;
-  int opt_tile_shift = 4;
+  int opt_tile_shift = 9;
+  int opt_length_bins = 512;
+  // mesh extent, read once per (edgex, edgey) pair for the sort's history-length estimate
+  const double* mesh_ex = nullptr;
+  const double* mesh_ey = nullptr;
+  double mesh_width = 1.0, mesh_height = 1.0;
   uint64_t launches = 0;
   uint64_t last_stats[8] = {0};
   int opt_print = 1;
@@ -372,6 +377,18 @@ void run_step(Bank* bank, int nx, int ny, uint64_t master_key, double dt, int nt
   CU_FATAL(cudaMemsetAsync(g.d_totals, 0, sizeof(unsigned long long) * kTotCount, g.stream));
   CU_FATAL(cudaEventRecord(g.ev_begin, g.stream));
   if (g.opt_pipeline) {
+    if (g.mesh_ex != edgex || g.mesh_ey != edgey) {  // extent of the mesh (a scheduling hint)
+      double ex[2], ey[2];
+      CU_FATAL(cudaMemcpyAsync(&ex[0], edgex, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+      CU_FATAL(cudaMemcpyAsync(&ex[1], edgex + nx, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+      CU_FATAL(cudaMemcpyAsync(&ey[0], edgey, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+      CU_FATAL(cudaMemcpyAsync(&ey[1], edgey + ny, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+      CU_FATAL(cudaStreamSynchronize(g.stream));
+      g.mesh_ex = edgex;
+      g.mesh_ey = edgey;
+      g.mesh_width = ex[1] > ex[0] ? ex[1] - ex[0] : 1.0;
+      g.mesh_height = ey[1] > ey[0] ? ey[1] - ey[0] : 1.0;
+    }
     // P0: restage the read-only inputs (cross-section tables, density tile map)
     stage_tables(a);
     stage_tiles(a);
@@ -380,7 +397,11 @@ void run_step(Bank* bank, int nx, int ny, uint64_t master_key, double dt, int nt
     s.tile_shift = g.opt_tile_shift;
     s.tiles_x = s.tile_shift >= 0 ? ((nx - 1) >> s.tile_shift) + 1 : 1;
     s.ntiles = s.tile_shift >= 0 ? s.tiles_x * (((ny - 1) >> s.tile_shift) + 1) : 1;
-    s.nbins = 3 * s.ntiles + 1;
+    s.nq = g.opt_length_bins > 1 ? g.opt_length_bins : 1;
+    s.q_scale = 24.0f;  // 12 bins across the sqrt(2) spread of facet counts with direction
+    s.inv_dx = (float)((double)nx / g.mesh_width);
+    s.inv_dy = (float)((double)ny / g.mesh_height);
+    s.nbins = 3 * s.nq * s.ntiles + 1;
     s.n_upper = bank->n_upper;
     s.n = bank->n;
     if (!bank->has_alt) {
@@ -938,6 +959,7 @@ extern "C" int nb200_set_option(const char* name, int value) {
   else if (strcmp(name, "pipeline") == 0) slot = &g.opt_pipeline;
   else if (strcmp(name, "fast_div") == 0) slot = &g.opt_fast_div;
   else if (strcmp(name, "tile_shift") == 0) slot = &g.opt_tile_shift;
+  else if (strcmp(name, "length_bins") == 0) slot = &g.opt_length_bins;
   if (!slot) {
     set_error("nb200_set_option: unknown option '%s'", name);
     return -3;

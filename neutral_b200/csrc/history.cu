@@ -50,8 +50,9 @@ enum : unsigned {
   kFlagSpeedOk = 1u,      // the speed is inside the proven range of div_by_known
   kFlagCellMfpOk = 2u,    // so is the cell mean free path
   kFlagDivOk = kFlagSpeedOk | kFlagCellMfpOk,
-  kFlagCoarseMixed = 4u,  // the current 64x64 tile is not uniform: consult the fine map
+  kFlagCoarseMixed = 4u,  // the current coarse tile is not uniform: consult the fine map
   kFlagFineMixed = 8u,    // nor is the current 16x16 tile: densities come from the mesh
+  kFlagAnyMixed = kFlagCoarseMixed | kFlagFineMixed,
   kFlagPending = 16u,     // collisions deposited energy that no tally flush has taken yet
   kFlagDead = 32u,
 };
@@ -88,6 +89,14 @@ __device__ __forceinline__ void derive(const StepArgs& a, double e, double nd, D
 // exactly zero (omp3/neutral.c:333-366 tests > 0 and < 0 separately).
 __device__ __forceinline__ int axis_step(double o) { return (o > 0.0) ? 1 : ((o < 0.0) ? -1 : 0); }
 
+// The same step read off ui = 1 / (o * speed), which the loop already holds: ui has the sign
+// of o, and is infinite exactly when o is zero (the speed is positive and finite).
+__device__ __forceinline__ int axis_step_from_reciprocal(double ui) {
+  const int hi = __double2hiint(ui);
+  const int s = (hi >> 31) | 1;
+  return ((unsigned)(hi & 0x7fffffff) >= 0x7ff00000u) ? 0 : s;
+}
+
 // The edge a particle in cell c is heading for (omp3/neutral.c:442-444, 448-450): the far
 // edge when the direction component is >= 0, else the near edge pulled in by
 // OPEN_BOUND_CORRECTION.
@@ -111,6 +120,7 @@ struct Parked {
   double p_absorb[kHistoryThreads];
   double rho[kHistoryThreads];
   double edep[kHistoryThreads];
+  int origin[kHistoryThreads];  // index in injection order: RNG key and counter slot
 };
 
 template <bool kFastDiv>
@@ -121,6 +131,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
 #define PARKED(name) park.name[threadIdx.x]
 #else
   double park_e, park_Sig_s, park_p_absorb, park_rho, park_edep;
+  int park_origin;
 #define PARKED(name) park_##name
 #endif
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -142,6 +153,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
     unsigned flags = 0;
     PARKED(e) = ew.x;
     PARKED(edep) = 0.0;
+    PARKED(origin) = m.w;
     // RNG counter: k_begin_step drew counter 0 (omp3/neutral.c:129); collision number k of
     // this step draws counters 2k-1 and 2k (:235, :294), so the collision count nc is the
     // counter state.
@@ -170,9 +182,8 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
     double uxi = 1.0 / (ox * v);
     double uyi = 1.0 / (oy * v);
     // ---- ... and the edges the particle is heading for (change when it crosses or turns)
-    int sx = axis_step(ox), sy = axis_step(oy);
-    double ex = target_edge(a.edgex, cx, sx);
-    double ey = target_edge(a.edgey, cy, sy);
+    double ex = target_edge(a.edgex, cx, axis_step(ox));
+    double ey = target_edge(a.edgey, cy, axis_step(oy));
 
     while (dtc > 0.0) {
       // calc_distance_to_facet, omp3/neutral.c:423-471
@@ -189,11 +200,11 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
         // :332-368 on the crossed axis only: step one cell, or reflect at the mesh boundary.
         // Decided first so that the next target edge is in flight during the arithmetic.
         const int c = x_facet ? cx : cy;
-        const int s = x_facet ? sx : sy;
+        const int s = axis_step_from_reciprocal(x_facet ? uxi : uyi);
         const int cn = c + s;
         const bool reflect = (unsigned)cn >= (unsigned)(x_facet ? a.nx : a.ny);
-        const double e_next = target_edge(x_facet ? a.edgex : a.edgey, reflect ? c : cn,
-                                          reflect ? -s : s);
+        const bool up_next = (reflect ? -s : s) >= 0;
+        double e_next = __ldg((x_facet ? a.edgex : a.edgey) + (reflect ? c : cn) + (up_next ? 1 : 0));
         nf++;
         double q_mfp, q_dtc;
         if (kFastDiv && (flags & kFlagDivOk) == kFlagDivOk && safe_exponent(d_facet)) {
@@ -215,38 +226,48 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
         atomicAdd(a.tally + cell, edep * a.inv_ntotal);
         x += d_facet * ox;
         y += d_facet * oy;
+        // the edge load is consumed here, after the arithmetic it overlapped with
+        asm volatile("" : "+d"(e_next));
+        if (!up_next) e_next -= kOpenBoundCorrection;
         if (x_facet) ex = e_next; else ey = e_next;
         if (reflect) {
-          if (x_facet) { ox = -ox; uxi = -uxi; sx = -sx; } else { oy = -oy; uyi = -uyi; sy = -sy; }
+          if (x_facet) { ox = -ox; uxi = -uxi; } else { oy = -oy; uyi = -uyi; }
         } else {
           if (x_facet) { cx = cn; cell += s; } else { cy = cn; cell += s * a.nx; }
           // :372-378 - the macroscopic cross sections follow the density of the new cell.
           // Inside a uniform coarse tile the density cannot change; otherwise the coarse map,
           // the fine map and finally the mesh itself are consulted.
           const int crossed = cn ^ c;
-          if ((crossed >> kCoarseShift) ||
-              (flags & kFlagFineMixed) ||
-              ((flags & kFlagCoarseMixed) && (crossed >> kTileShift))) {
-            double rho_new = PARKED(rho);
+          if ((crossed >> kCoarseShift) || (flags & kFlagAnyMixed)) {
+            double rho_new;
+            bool known = false;
             if (crossed >> kCoarseShift) {
-              const double t = coarse_value(a, cx, cy);
-              if (is_mixed_tile(t)) {
+              rho_new = coarse_value(a, cx, cy);
+              // common case: from one uniform coarse tile into another of the same density
+              if (!(flags & kFlagAnyMixed) &&
+                  double_to_bits(rho_new) == double_to_bits(PARKED(rho)))
+                continue;
+              if (is_mixed_tile(rho_new)) {
                 flags |= kFlagCoarseMixed;
               } else {
-                flags &= ~(kFlagCoarseMixed | kFlagFineMixed);
-                rho_new = t;
+                flags &= ~kFlagAnyMixed;
+                known = true;
               }
             }
-            if ((flags & kFlagCoarseMixed) && (crossed >> kTileShift)) {
-              const double t = fine_value(a, cx, cy);
-              if (is_mixed_tile(t)) {
-                flags |= kFlagFineMixed;
-              } else {
-                flags &= ~kFlagFineMixed;
-                rho_new = t;
+            if (!known && (flags & kFlagCoarseMixed)) {
+              if ((crossed >> kTileShift) || (crossed >> kCoarseShift)) {
+                rho_new = fine_value(a, cx, cy);
+                if (is_mixed_tile(rho_new)) {
+                  flags |= kFlagFineMixed;
+                } else {
+                  flags &= ~kFlagFineMixed;
+                  known = true;
+                }
+              } else if (!(flags & kFlagFineMixed)) {
+                continue;  // still inside the same uniform fine tile
               }
             }
-            if (flags & kFlagFineMixed) rho_new = __ldg(a.density + cell);
+            if (!known) rho_new = __ldg(a.density + cell);  // mixed fine tile: the mesh itself
             if (double_to_bits(rho_new) != double_to_bits(PARKED(rho))) {
               PARKED(rho) = rho_new;
               nd = number_density(rho_new);
@@ -257,7 +278,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
       } else if (collide) {
         // ---- collision_event, :209-300
         nc++;
-        const uint64_t pkey = a.pid0 + (uint64_t)(unsigned)m.w;
+        const uint64_t pkey = a.pid0 + (uint64_t)(unsigned)PARKED(origin);
         const double e = PARKED(e);
         const double p_absorb = PARKED(p_absorb);
         const double edep = PARKED(edep) + deposition(w, d_coll, d.stb, d.heat, nd);  // :222-225
@@ -298,10 +319,8 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
           flags = safe_exponent(v) ? (flags | kFlagSpeedOk) : (flags & ~kFlagSpeedOk);
           uxi = 1.0 / (ox * v);
           uyi = 1.0 / (oy * v);
-          sx = axis_step(ox);
-          sy = axis_step(oy);
-          ex = target_edge(a.edgex, cx, sx);
-          ey = target_edge(a.edgey, cy, sy);
+          ex = target_edge(a.edgex, cx, axis_step(ox));
+          ey = target_edge(a.edgey, cy, axis_step(oy));
         }
         PARKED(edep) = edep;
         flags |= kFlagPending;
@@ -326,10 +345,11 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
     a.bank.dir[slot] = make_double2(ox, oy);
     a.bank.ew[slot] = make_double2(PARKED(e), w);
     a.bank.tm[slot] = make_double2(dtc, mfp);
-    a.bank.meta[slot] = make_int4(cx, cy, (int)died, m.w);
-    if (a.p_facets) a.p_facets[m.w] += nf;
-    if (a.p_collisions) a.p_collisions[m.w] += nc;
-    if (a.p_census) a.p_census[m.w] += census;
+    const int origin = PARKED(origin);
+    a.bank.meta[slot] = make_int4(cx, cy, (int)died, origin);
+    if (a.p_facets) a.p_facets[origin] += nf;
+    if (a.p_collisions) a.p_collisions[origin] += nc;
+    if (a.p_census) a.p_census[origin] += census;
   }
   flush_totals(a.totals, nf, nc, processed, census, died);
 #undef PARKED

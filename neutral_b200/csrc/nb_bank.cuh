@@ -68,12 +68,12 @@ struct CsStage {
 
 // Density tile maps, rebuilt every timestep (stage.cu). fine[t] holds the density of the
 // 16x16-cell tile t when all its cells carry the same bit pattern, else the kMixedTileBits
-// marker; coarse[] is the same over 64x64-cell tiles (uniform iff its fine tiles are uniform
-// and equal). A facet crossing inside a uniform coarse tile needs no memory access at all;
-// the 31 KB coarse map stays L1-resident, the fine map L2-resident, and only mixed fine
+// marker; coarse[] is the same over 128x128-cell tiles (uniform iff its fine tiles are
+// uniform and equal). A facet crossing inside a uniform coarse tile needs no memory access at
+// all; the 8 KB coarse map stays L1-resident, the fine map L2-resident, and only mixed fine
 // tiles read the density mesh itself.
 constexpr int kTileShift = 4;
-constexpr int kCoarseShift = 6;
+constexpr int kCoarseShift = 7;
 constexpr unsigned long long kMixedTileBits = 0x7ff8b200dead0001ull;  // a NaN payload of ours
 struct TileMap {
   const double* fine;
@@ -119,7 +119,10 @@ struct SortArgs {
   unsigned* bin_cursor;  // [nbins] running destination of every bin
   unsigned* chunk_sum;   // [ceil(nbins / 2048)] scratch of the histogram scan
   unsigned* n_live;      // device scalar: slots in front of the dead bin after the sort
-  int nbins;             // 3 classes x ntiles + 1 dead bin
+  int nbins;             // 3 classes x nq length bins x ntiles + 1 dead bin
+  int nq;                // bins of expected history length (1: none)
+  float q_scale;         // length bins per octave
+  float inv_dx, inv_dy;  // cells per unit length (mean over the mesh)
   int ntiles;
   int tiles_x;
   int tile_shift;        // cells per tile edge = 1 << tile_shift; < 0: one tile

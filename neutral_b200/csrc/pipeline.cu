@@ -8,8 +8,10 @@
 //                     classification by NEXT EVENT TYPE (collision / facet / census) and
 //                     mesh tile, histogram of the sort keys (warp-aggregated atomics).
 //   P2 k_scan_bins    exclusive scan of the histogram -> bin offsets.
-//   P3 k_scatter      stable-enough counting sort of the bank into its double buffer:
-//                     colliders first (longest histories), then streamers by tile, census,
+//   P3 k_scatter      counting sort of the bank into its double buffer: colliders first,
+//                     then streamers, then census-only particles; inside a class by
+//                     expected history length (longest first, so that the lanes of a warp
+//                     finish together and the long histories start early) and mesh tile;
 //                     dead particles compacted to the tail. Warp ballot/match aggregation.
 //   P4 k_history      (history.cu) event loop to census/death on event-type-coherent warps.
 //
@@ -87,7 +89,23 @@ __global__ void __launch_bounds__(256) k_begin_step(const StepArgs a, const Sort
       const unsigned tile = s.tile_shift >= 0
                                 ? (unsigned)((cy >> s.tile_shift) * s.tiles_x + (cx >> s.tile_shift))
                                 : 0u;
-      key = (unsigned)cls * (unsigned)s.ntiles + tile;
+      // Expected number of events of this history until census, a scheduling hint only
+      // (single precision, never feeds back into a particle): streamers cross about
+      // (|omega_x|/dx + |omega_y|/dy) * speed * dt facets; a collider scatters its energy
+      // down by ~2 % per scatter (omp3/neutral.c:265-267 averaged over mu) and is absorbed
+      // as often as it scatters until it falls below MIN_ENERGY_OF_INTEREST (:243).
+      unsigned qbin = 0;
+      if (s.nq > 1) {
+        float est = 1.0f;
+        if (cls == kClsFacet)
+          est += (fabsf((float)dir.x) * s.inv_dx + fabsf((float)dir.y) * s.inv_dy) *
+                 (float)v * (float)a.dt;
+        else if (cls == kClsCollision)
+          est += 101.0f * __logf(fmaxf((float)e, 1.0f));
+        const int q = (int)(__log2f(est) * s.q_scale);
+        qbin = (unsigned)(s.nq - 1 - min(max(q, 0), s.nq - 1));  // longest histories first
+      }
+      key = ((unsigned)cls * (unsigned)s.nq + qbin) * (unsigned)s.ntiles + tile;
     }
     s.keys[slot] = key;
   }

@@ -29,10 +29,10 @@ def _hashes(bank):
 
 
 MODES = {
-    "pipeline": dict(pipeline=1, fast_div=1, tile_shift=4),      # the default
-    "pipeline-ieee-div": dict(pipeline=1, fast_div=0, tile_shift=2),
-    "pipeline-class-only": dict(pipeline=1, fast_div=1, tile_shift=-1),
-    "direct": dict(pipeline=0, fast_div=0, tile_shift=4),
+    "pipeline": dict(pipeline=1, fast_div=1, tile_shift=9, length_bins=512),   # the default
+    "pipeline-ieee-div": dict(pipeline=1, fast_div=0, tile_shift=2, length_bins=16),
+    "pipeline-class-only": dict(pipeline=1, fast_div=1, tile_shift=-1, length_bins=1),
+    "direct": dict(pipeline=0, fast_div=0, tile_shift=9, length_bins=512),
 }
 
 
