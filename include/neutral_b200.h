@@ -183,13 +183,18 @@ int nb200_synchronize(void);
 /* dst[i] += src[i] on the device: combines per-step tally deltas of a particle-sharded run
  * (after the all-reduce of the deltas). */
 int nb200_accumulate(double* dst_device, const double* src_device, size_t n);
+/* The same, and src[i] = 0 afterwards (the delta buffer is ready for its next timestep). */
+int nb200_accumulate_clear(double* dst_device, double* src_device, size_t n);
 
 /* Options: "print" (1: print the reference's "Particles" line); "pipeline" (1, default:
  * phased timestep - begin-step/classify, counting sort by next-event type and tile, event
  * loop; 0: the direct one-thread-per-history kernel on the unsorted bank); "fast_div"
  * (1, default: exact division by loop-invariant divisors through their reciprocals);
  * "tile_shift" (log2 of the sort tile edge in cells, default 9; < 0: no spatial key);
- * "length_bins" (bins of expected history length in the sort key, default 512; <= 1: none).
+ * "length_bins" (bins of expected history length in the sort key, default 512; <= 1: none);
+ * "tally_prereduce" (1: combine same-cell tally flushes of a warp with shuffles before the
+ * atomic; default 0); "l2_persist" (1: the history kernel's launch carries an access-policy
+ * window that keeps the staged cross-section tables persisting in L2; default 0).
  * Returns the previous value, or a negative code for an unknown name. */
 int nb200_set_option(const char* name, int value);
 

@@ -85,6 +85,9 @@ struct Context {
   int opt_fast_div = 1;
   int opt_tile_shift = 9;
   int opt_length_bins = 512;
+  int opt_tally_prereduce = 0;
+  int opt_l2_persist = 0;
+  bool l2_limit_set = false;
   // mesh extent, read once per (edgex, edgey) pair for the sort's history-length estimate
   const double* mesh_ex = nullptr;
   const double* mesh_ey = nullptr;
@@ -389,6 +392,10 @@ void run_step(Bank* bank, int nx, int ny, uint64_t master_key, double dt, int nt
       g.mesh_width = ex[1] > ex[0] ? ex[1] - ex[0] : 1.0;
       g.mesh_height = ey[1] > ey[0] ? ey[1] - ey[0] : 1.0;
     }
+    if (g.opt_l2_persist && !g.l2_limit_set) {  // set-aside for the persisting window
+      CU_FATAL(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 4u << 20));
+      g.l2_limit_set = true;
+    }
     // P0: restage the read-only inputs (cross-section tables, density tile map)
     stage_tables(a);
     stage_tiles(a);
@@ -425,7 +432,10 @@ void run_step(Bank* bank, int nx, int ny, uint64_t master_key, double dt, int nt
     a.bank = bank->cur;
     CU_FATAL(cudaEventRecord(g.ev_mid, g.stream));
     // P4: event loop over the sorted live prefix
-    g.launches += launch_history(a, g.d_n_live, s.n_upper, g.opt_fast_div != 0, g.stream);
+    g.launches += launch_history(a, g.d_n_live, s.n_upper, g.opt_fast_div != 0,
+                                 g.opt_tally_prereduce != 0,
+                                 g.opt_l2_persist ? g.d_cs_stage : nullptr, g.cs_stage_bytes,
+                                 g.stream);
   } else {
     CU_FATAL(cudaEventRecord(g.ev_mid, g.stream));
     g.launches += launch_history_direct(a, g.stream);
@@ -850,6 +860,12 @@ extern "C" int nb200_accumulate(double* dst_device, const double* src_device, si
   return 0;
 }
 
+extern "C" int nb200_accumulate_clear(double* dst_device, double* src_device, size_t n) {
+  if (ensure_ready() != 0) return -1;
+  g.launches += launch_accumulate_clear(dst_device, src_device, n, g.stream);
+  return 0;
+}
+
 extern "C" int nb200_bank_export(nb200_particle_soa* particles) {
   if (ensure_ready() != 0) return -1;
   Bank* bank = bank_of(particles);
@@ -960,6 +976,8 @@ extern "C" int nb200_set_option(const char* name, int value) {
   else if (strcmp(name, "fast_div") == 0) slot = &g.opt_fast_div;
   else if (strcmp(name, "tile_shift") == 0) slot = &g.opt_tile_shift;
   else if (strcmp(name, "length_bins") == 0) slot = &g.opt_length_bins;
+  else if (strcmp(name, "tally_prereduce") == 0) slot = &g.opt_tally_prereduce;
+  else if (strcmp(name, "l2_persist") == 0) slot = &g.opt_l2_persist;
   if (!slot) {
     set_error("nb200_set_option: unknown option '%s'", name);
     return -3;

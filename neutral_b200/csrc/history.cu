@@ -123,7 +123,26 @@ struct Parked {
   int origin[kHistoryThreads];  // index in injection order: RNG key and counter slot
 };
 
-template <bool kFastDiv>
+// update_tallies (omp3/neutral.c:408-420). With kPreReduce the lanes of the warp that flush
+// into the same cell at the same moment are combined with shuffles first and their leader
+// issues one atomic (north_star phase 5). Off by default: measured, it loses - see DESIGN.md 4.
+template <bool kPreReduce>
+__device__ __forceinline__ void tally_add(double* __restrict__ tally, int cell, double value) {
+  if (kPreReduce) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(__activemask(), cell);
+    if (peers != (1u << lane)) {
+      double sum = 0.0;
+      for (unsigned rest = peers; rest; rest &= rest - 1)
+        sum += __shfl_sync(peers, value, __ffs(rest) - 1);
+      if (lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(tally + cell, sum);
+      return;
+    }
+  }
+  atomicAdd(tally + cell, value);
+}
+
+template <bool kFastDiv, bool kPreReduce>
 __global__ void __launch_bounds__(kHistoryThreads, NB_HISTORY_MIN_BLOCKS)
 k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
 #if NB_PARK_SMEM
@@ -223,7 +242,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
           PARKED(edep) = 0.0;
           flags &= ~kFlagPending;
         }
-        atomicAdd(a.tally + cell, edep * a.inv_ntotal);
+        tally_add<kPreReduce>(a.tally, cell, edep * a.inv_ntotal);
         x += d_facet * ox;
         y += d_facet * oy;
         // the edge load is consumed here, after the arithmetic it overlapped with
@@ -296,7 +315,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
           w *= (1.0 - p_absorb);
           if (e < kMinEnergyOfInterest) {  // :243-252 - the history ends here
             flags |= kFlagDead;
-            atomicAdd(a.tally + cell, edep * a.inv_ntotal);
+            tally_add<kPreReduce>(a.tally, cell, edep * a.inv_ntotal);
             break;
           }
           // Energy and direction are unchanged: the lookups of :285-291 return the values
@@ -334,7 +353,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
         mfp -= d_census / d.cell_mfp;
         double edep = deposition(w, d_census, d.stb, d.heat, nd);
         if (flags & kFlagPending) edep = PARKED(edep) + edep;
-        atomicAdd(a.tally + cell, edep * a.inv_ntotal);
+        tally_add<kPreReduce>(a.tally, cell, edep * a.inv_ntotal);
         dtc = 0.0;
         break;
       }
@@ -357,14 +376,33 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
 
 static inline int blocks_for(int n, int threads) { return (n + threads - 1) / threads; }
 
+// `pin`/`pin_bytes` (optional) name the staged cross-section block: the launch then carries an
+// access-policy window that keeps it persisting in L2 (north_star phase 3), while the rest of
+// the kernel's traffic - the tally atomics above all - streams through the remainder.
 int launch_history(const StepArgs& a, const unsigned* n_live, int n_upper, bool fast_div,
-                   cudaStream_t st) {
+                   bool prereduce, const void* pin, size_t pin_bytes, cudaStream_t st) {
   if (n_upper <= 0) return 0;
-  const int blocks = blocks_for(n_upper, kHistoryThreads);
-  if (fast_div)
-    k_history<true><<<blocks, kHistoryThreads, 0, st>>>(a, n_live);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks_for(n_upper, kHistoryThreads));
+  cfg.blockDim = dim3(kHistoryThreads);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (pin && pin_bytes) {
+    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(pin);
+    attr[0].val.accessPolicyWindow.num_bytes = pin_bytes;
+    attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+    attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  if (prereduce)
+    cudaLaunchKernelEx(&cfg, k_history<true, true>, a, n_live);
+  else if (fast_div)
+    cudaLaunchKernelEx(&cfg, k_history<true, false>, a, n_live);
   else
-    k_history<false><<<blocks, kHistoryThreads, 0, st>>>(a, n_live);
+    cudaLaunchKernelEx(&cfg, k_history<false, false>, a, n_live);
   return 1;
 }
 

@@ -282,6 +282,25 @@ __global__ void k_accumulate(double* __restrict__ dst, const double* __restrict_
   if (i < n) dst[i] += src[i];
 }
 
+// dst += src; src = 0: folds a reduced per-step delta into the cumulative tally and leaves the
+// delta buffer ready for its next timestep in the same pass.
+__global__ void k_accumulate_clear(double* __restrict__ dst, double* __restrict__ src, size_t n) {
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 2;
+  for (; i + 1 < n; i += stride) {
+    double2 d = *reinterpret_cast<double2*>(dst + i);
+    const double2 s = *reinterpret_cast<const double2*>(src + i);
+    d.x += s.x;
+    d.y += s.y;
+    *reinterpret_cast<double2*>(dst + i) = d;
+    *reinterpret_cast<double2*>(src + i) = make_double2(0.0, 0.0);
+  }
+  if (i < n) {
+    dst[i] += src[i];
+    src[i] = 0.0;
+  }
+}
+
 // --------------------------------------------------------------------------------------
 // Launch wrappers
 // --------------------------------------------------------------------------------------
@@ -320,6 +339,12 @@ int launch_export_aos(BankView b, void* aos, int n, cudaStream_t st) {
 int launch_accumulate(double* dst, const double* src, size_t n, cudaStream_t st) {
   if (n == 0) return 0;
   k_accumulate<<<148 * 8, 256, 0, st>>>(dst, src, n);
+  return 1;
+}
+
+int launch_accumulate_clear(double* dst, double* src, size_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  k_accumulate_clear<<<148 * 8, 256, 0, st>>>(dst, src, n);
   return 1;
 }
 

@@ -15,7 +15,7 @@ int launch_history_direct(const StepArgs& a, cudaStream_t st);
 int launch_sort_phase(const StepArgs& a, const SortArgs& s, const BankView& alt,
                       cudaStream_t st);
 int launch_history(const StepArgs& a, const unsigned* n_live, int n_upper, bool fast_div,
-                   cudaStream_t st);
+                   bool prereduce, const void* pin, size_t pin_bytes, cudaStream_t st);
 // Per-step staging of the read-only inputs (stage.cu).
 int launch_stage_cs(const double* keys, const double* vals, int n, double2* kv, int* bucket,
                     unsigned long long bits0, int shift, int nb, const double* twin_keys,
@@ -32,6 +32,7 @@ int launch_import_aos(BankView b, const void* aos, int n, cudaStream_t st);
 int launch_export_aos(BankView b, void* aos, int n, cudaStream_t st);
 
 int launch_accumulate(double* dst, const double* src, size_t n, cudaStream_t st);
+int launch_accumulate_clear(double* dst, double* src, size_t n, cudaStream_t st);
 
 int launch_selftest_rng_log(uint64_t pkey0, uint64_t master_key, uint64_t counter, int n,
                             const LogTable* logt, uint64_t* raw, double* unit,

@@ -44,7 +44,7 @@ EXPORTED_SYMBOLS = [
     "nb200_solve_transport_2d_host",
     "nb200_abi_version", "nb200_last_error", "nb200_device_count", "nb200_set_stream",
     "nb200_set_shard", "nb200_bank_create", "nb200_bank_download", "nb200_bank_export",
-    "nb200_bank_upload", "nb200_accumulate", "nb200_bank_copy", "nb200_bank_size", "nb200_bank_free", "nb200_memcpy_h2d",
+    "nb200_bank_upload", "nb200_accumulate", "nb200_accumulate_clear", "nb200_bank_copy", "nb200_bank_size", "nb200_bank_free", "nb200_memcpy_h2d",
     "nb200_memcpy_d2h", "nb200_memset_d", "nb200_synchronize", "nb200_set_option",
     "nb200_last_step_stats", "nb200_kernel_launches", "nb200_selftest_rng_log",
     "nb200_selftest_log", "nb200_selftest_div", "nb200_selftest_cs", "nb200_host_threefry2x64_20",
@@ -96,6 +96,7 @@ def load_library(build: bool = False) -> C.CDLL:
     L.nb200_bank_export.argtypes = [_soa_p]
     L.nb200_bank_upload.argtypes = [_soa_p, _soa_p]
     L.nb200_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.nb200_accumulate_clear.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.nb200_bank_copy.argtypes = [_soa_p, _soa_p]
     L.nb200_bank_size.argtypes = [_soa_p]
     L.nb200_bank_free.argtypes = [_soa_p]

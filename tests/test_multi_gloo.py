@@ -1,0 +1,117 @@
+"""The multi-GPU host logic on CPU: world size 2 (and 3) over ``gloo``.
+
+Each rank drives ``neutral_b200.multi.run_timesteps`` - the loop ``bench.py`` uses under
+torchrun - with the oracle port as its per-rank engine (the CUDA engine needs a GPU): the
+contiguous particle shard of ``shard_range``, global RNG keys, per-timestep tally deltas
+combined by one all-reduce, with and without overlapping the reduction with the next
+timestep. The combined result must equal the single-rank run: exact event counts per
+timestep, bit-identical shard banks, tally within 1e-12 (summation order only)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from neutral_b200.decks import build_problem, shard_range  # noqa: E402
+from neutral_b200.multi import StepCounts, global_counts, run_timesteps  # noqa: E402
+
+
+class OracleShardEngine:
+    """ShardEngine over the CPU oracle (test infrastructure)."""
+
+    def __init__(self, prob, rank, world):
+        from oracle.oracle import OraclePort
+        self.port = OraclePort()
+        self.prob = prob
+        d = prob.deck
+        self.pid0, self.count = shard_range(d.nparticles, rank, world)
+        self.bank = self.port.inject(prob, self.pid0, self.count)
+        self.tally = np.zeros(d.nx * d.ny)
+        self.delta = [torch.zeros(d.nx * d.ny, dtype=torch.float64) for _ in range(2)]
+
+    def step_into_delta(self, tt, k):
+        assert not self.delta[k].any(), "delta buffer must be clear on entry"
+        before = int(np.count_nonzero(self.bank.dead == 0))
+        f, c, p = self.port.step(self.prob, self.bank, tt, self.delta[k].numpy(), pid0=self.pid0)
+        after = int(np.count_nonzero(self.bank.dead == 0))
+        assert p == before
+        return StepCounts(f, c, p, census=after, deaths=before - after)
+
+    def delta_tensor(self, k):
+        return self.delta[k]
+
+    def accumulate_and_clear(self, k):
+        self.tally += self.delta[k].numpy()
+        self.delta[k].zero_()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, deck, overlap, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        prob = build_problem(deck)
+        eng = OracleShardEngine(prob, rank, world)
+        local = run_timesteps(eng, prob.deck.iterations, world, dist, overlap=overlap)
+        total = global_counts(local, world, dist)
+        # every rank must hold the same cumulative tally
+        t = torch.from_numpy(eng.tally.copy())
+        lo, hi = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert torch.equal(lo, hi), "ranks disagree on the reduced tally"
+        np.savez(os.path.join(out, f"rank{rank}.npz"), tally=eng.tally,
+                 counts=np.array([[c.facets, c.collisions, c.processed, c.census, c.deaths]
+                                  for c in total]),
+                 pid0=eng.pid0, **{f"bank_{k}": v for k, v in eng.bank.arrays.items()})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,deck,overlap", [(2, "mixed_small", True), (2, "csp_small", False),
+                                                (3, "split_small", True)])
+def test_sharded_timesteps_over_gloo(tmp_path, port, world, deck, overlap):
+    mp.spawn(_worker, args=(world, _free_port(), deck, overlap, str(tmp_path)), nprocs=world,
+             join=True)
+    prob = build_problem(deck)
+    d = prob.deck
+    bank = port.inject(prob)
+    tally = np.zeros(d.nx * d.ny)
+    want = []
+    for tt in range(1, d.iterations + 1):
+        before = int(np.count_nonzero(bank.dead == 0))
+        f, c, p = port.step(prob, bank, tt, tally)
+        after = int(np.count_nonzero(bank.dead == 0))
+        want.append([f, c, p, after, before - after])
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
+        assert np.array_equal(got["counts"], np.array(want)), f"rank {r}: global counts"
+        pid0, count = shard_range(d.nparticles, r, world)
+        assert int(got["pid0"]) == pid0
+        for k, v in bank.arrays.items():
+            assert got[f"bank_{k}"].tobytes() == v[pid0:pid0 + count].tobytes(), (r, k)
+        t = got["tally"]
+        assert np.all(np.abs(t - tally) <= 1e-12 * np.maximum(np.abs(t), np.abs(tally)))
+
+
+def test_shard_ranges_tile_the_bank():
+    for n, world in [(10, 3), (1_000_000, 8), (7, 8), (100_000_000, 8)]:
+        nxt = 0
+        for r in range(world):
+            first, count = shard_range(n, r, world)
+            assert first == nxt and count in (n // world, n // world + 1)
+            nxt = first + count
+        assert nxt == n
