@@ -12,7 +12,8 @@ injected bank. Prints ONE JSON line (rank 0):
                 timed steps / device time, max over ranks ), inputs resident in HBM;
 * ``e2e``       the same metric with HOST buffers: every step uploads the deck (mesh,
                 cross sections, bank) from pinned host memory, runs the timesteps through
-                solve_transport_2d, and reads tally, bank and counters back;
+                solve_transport_2d, and reads tally and bank back (double-buffered: the
+                copies of neighbouring steps overlap a step's transport);
 * ``roofline``  the history kernel against the measured HBM peak, algorithmic bytes per
                 event from SURVEY.md 8d (facet 200 B, collision 176 B, census 192 B, fatal
                 collision +16 B);
@@ -46,6 +47,7 @@ METRIC = "particle_events_per_sec"
 UNIT = "events/s"
 # algorithmic bytes per event of the event-based model
 B_FACET, B_COLLISION, B_CENSUS, B_DEATH_EXTRA = 200.0, 176.0, 192.0, 16.0
+RED_PEAK_PER_S = 1.9e11  # measured: spread-address red.global.add.f64, L2-resident footprint
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
@@ -322,45 +324,95 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
     tally_sum = float(torch.from_numpy(sim.tally_to_host()).sum()) if rank == 0 else 0.0
 
     # ---- e2e: host buffers in, host buffers out, every step ---------------------------
+    # Every step uploads ALL of its inputs (mesh, edges, cross-section tables, bank) from
+    # pinned host memory and downloads its results (tally, bank) to pinned host memory. The
+    # steps are independent, so the transfers are double-buffered the way a production host
+    # would: two device-side working sets; while step i transports on set i%2, the upload of
+    # step i+1 and the download of step i-1 run on their own copy streams. Nothing is skipped:
+    # the timed region holds K full uploads, K full runs and K full downloads.
     e2e = None
     if not args.no_e2e:
+        from neutral_b200.bank import ALL_FIELDS, ParticleSoA
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         h_density, h_ex, h_ey = pin(prob.density.ravel()), pin(prob.edgex), pin(prob.edgey)
         h_cs = [pin(a) for pair in (prob.cs_scatter, prob.cs_absorb) for a in pair]
         h_bank = {k: pin(v) for k, v in start_bank.arrays.items()}
-        h_bank_struct = HostBank({k: v.numpy() for k, v in h_bank.items()}).as_struct()
-        out_tally = torch.empty(ncells, dtype=torch.float64).pin_memory()
-        out_bank = HostBank({k: torch.empty_like(v).pin_memory().numpy()
-                             for k, v in h_bank.items()})
-        out_struct = out_bank.as_struct()
-        dev_inputs = [(sim.density, h_density), (sim.edgex, h_ex), (sim.edgey, h_ey)] + \
-            list(zip(sim._cs_arrays, h_cs))
-        h2d = sum(t.numel() * t.element_size() for _, t in dev_inputs) + \
-            sum(t.numel() * t.element_size() for t in h_bank.values())
-        d2h = out_tally.numel() * 8 + sum(t.numel() * t.element_size() for t in h_bank.values())
+        nbytes = lambda t: t.numel() * t.element_size()
 
-        def e2e_step():
-            for dev, host in dev_inputs:
-                _check(lib.nb200_memcpy_h2d(dev.ptr, host.data_ptr(),
-                                            host.numel() * host.element_size()), "h2d")
-            _check(lib.nb200_bank_upload(sim.bank, C.byref(h_bank_struct)), "bank_upload")
-            sim.tally.zero()
-            out = timesteps()
-            _check(lib.nb200_memcpy_d2h(out_tally.data_ptr(), sim.tally.ptr, ncells * 8), "d2h")
-            _check(lib.nb200_bank_download(sim.bank, C.byref(out_struct)), "bank_download")
+        class WorkingSet:
+            def __init__(self, s):
+                self.sim = s
+                self.engine = GpuShardEngine(s, ncells) if world > 1 else None
+                self.view = ParticleSoA()
+                _check(lib.nb200_bank_view(s.bank, C.byref(self.view)), "bank_view")
+                self.inputs = [(s.density, h_density), (s.edgex, h_ex), (s.edgey, h_ey)] + \
+                    list(zip(s._cs_arrays, h_cs))
+                self.out_tally = torch.empty(ncells, dtype=torch.float64).pin_memory()
+                self.out_bank = {k: torch.empty_like(v).pin_memory() for k, v in h_bank.items()}
+                self.uploaded = torch.cuda.Event()
+                self.downloaded = torch.cuda.Event()
+
+            def field_ptr(self, k):
+                return C.cast(getattr(self.view, k), C.c_void_p).value
+
+        sim_b = Simulation(prob, rank=rank, nranks=world, per_particle_counters=False)
+        sim_b.load_bank(start_bank)
+        sets = [WorkingSet(sim), WorkingSet(sim_b)]
+        up, down = torch.cuda.Stream(), torch.cuda.Stream()
+        h2d = sum(nbytes(t) for _, t in sets[0].inputs) + sum(nbytes(t) for t in h_bank.values())
+        d2h = ncells * 8 + sum(nbytes(t) for t in h_bank.values())
+
+        def enqueue_upload(ws):
+            up.wait_event(ws.downloaded)  # the set's previous results must have left it
+            for dev, host in ws.inputs:
+                _check(lib.nb200_memcpy_h2d_async(dev.ptr, host.data_ptr(), nbytes(host),
+                                                  up.cuda_stream), "h2d")
+            for k in ALL_FIELDS:
+                _check(lib.nb200_memcpy_h2d_async(ws.field_ptr(k), h_bank[k].data_ptr(),
+                                                  nbytes(h_bank[k]), up.cuda_stream), "h2d bank")
+            ws.uploaded.record(up)
+
+        def transport(ws):
+            torch.cuda.current_stream().wait_event(ws.uploaded)
+            _check(lib.nb200_bank_import(ws.sim.bank), "bank_import")
+            ws.sim.tally.zero()
+            if world > 1:
+                out = run_timesteps(ws.engine, d.iterations, world, dist)
+            else:
+                out = [ws.sim.step(tt) for tt in range(1, d.iterations + 1)]
+            _check(lib.nb200_bank_export(ws.sim.bank), "bank_export")  # synchronises
             return out
 
-        for _ in range(min(args.warmup, 2)):
-            e2e_step()
+        def enqueue_download(ws):
+            _check(lib.nb200_memcpy_d2h_async(ws.out_tally.data_ptr(), ws.sim.tally.ptr,
+                                              ncells * 8, down.cuda_stream), "d2h")
+            for k in ALL_FIELDS:
+                _check(lib.nb200_memcpy_d2h_async(ws.out_bank[k].data_ptr(), ws.field_ptr(k),
+                                                  nbytes(h_bank[k]), down.cuda_stream), "d2h bank")
+            ws.downloaded.record(down)
+
+        def e2e_run(nsteps):
+            out = []
+            enqueue_upload(sets[0])
+            for i in range(nsteps):
+                if i + 1 < nsteps:
+                    enqueue_upload(sets[(i + 1) & 1])
+                out += transport(sets[i & 1])
+                enqueue_download(sets[i & 1])
+            up.synchronize()
+            down.synchronize()
+            return out
+
+        e2e_run(min(args.warmup, 2))
         fence()
         t0 = time.perf_counter()
-        e2e_res = []
-        for _ in range(args.steps):
-            e2e_res += e2e_step()
+        e2e_res = e2e_run(args.steps)
         fence()
         e2e_s = time.perf_counter() - t0
+        last = sets[(args.steps - 1) & 1]
         e2e = {"events": sum(r.events for r in e2e_res), "seconds": e2e_s, "h2d": h2d,
-               "d2h": d2h, "tally_sum": float(out_tally.sum())}
+               "d2h": d2h, "tally_sum": float(last.out_tally.sum()),
+               "live_out": int((last.out_bank["dead"] == 0).sum())}
 
     # ---- reduce over ranks -------------------------------------------------------------
     if world > 1:
@@ -399,7 +451,17 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
         # design keeps a history in registers for a whole timestep, so `frac` reads above 1.
         # The fused-history lower bound and the measured DRAM traffic say what HBM really sees.
         "fused_bound_bytes_per_launch": fused_history_bytes(timed) / max(hist_launches, 1),
-        "note": "k_history is FP64-issue/latency bound, not HBM bound (DESIGN.md 5)",
+        # The ceiling that does bind facet-dominated decks: every facet, census and death is one
+        # red.global.add.f64 into the tally, and the B200 L2 retires 1.9e11 of those per second
+        # (tools/microbench/red_rate.cu, profiles/r01/red_rate.txt).
+        "atomic_bound": {
+            "achieved": sum(r.facets + r.census + r.deaths for r in timed) / max(kernel_ns, 1) * 1e9,
+            "peak": RED_PEAK_PER_S, "unit": "fp64 reductions/s",
+            "frac": sum(r.facets + r.census + r.deaths for r in timed) / max(kernel_ns, 1) * 1e9
+            / RED_PEAK_PER_S,
+            "peak_source": "measured, profiles/r01/red_rate.txt"},
+        "note": "k_history is bound by L2 FP64 atomics (facets) and FP64 issue (collisions), "
+                "not by HBM (DESIGN.md 5)",
     }
     line = {
         "metric": METRIC, "value": events_all / (elapsed_ms / 1e3), "unit": UNIT,
@@ -425,7 +487,9 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
         line["e2e"] = {"value": e2e_events_all / e2e_seconds, "unit": UNIT,
                        "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                        "ms_per_step": 1e3 * e2e_seconds / args.steps,
-                       "tally_sum": e2e["tally_sum"]}
+                       "tally_sum": e2e["tally_sum"], "live_particles_out": e2e["live_out"],
+                       "pipeline": "double-buffered: upload of step i+1 and download of step "
+                                   "i-1 overlap the transport of step i"}
     if world == 1 and not args.no_cpu_baseline:
         try:
             res = reference_rate(args.deck, target_seconds=15.0)

@@ -169,6 +169,12 @@ int nb200_bank_download(nb200_particle_soa* particles, nb200_particle_soa* host)
 int nb200_bank_upload(nb200_particle_soa* particles, const nb200_particle_soa* host);
 /* Refreshes the plain device SoA view behind the handle's 11 pointers. */
 int nb200_bank_export(nb200_particle_soa* particles);
+/* The plain device SoA view behind the handle (11 device arrays of bank-size elements,
+ * allocated on first use), and the kernel that rebuilds the bank from it (asynchronous on
+ * the library's stream): a host that moves banks with its own asynchronous copies fills the
+ * view and calls nb200_bank_import, or calls nb200_bank_export and reads the view. */
+int nb200_bank_view(nb200_particle_soa* particles, nb200_particle_soa* view_out);
+int nb200_bank_import(nb200_particle_soa* particles);
 /* Overwrites the bank's state from another bank of the same size (device to device). */
 int nb200_bank_copy(nb200_particle_soa* dst, nb200_particle_soa* src);
 int nb200_bank_size(nb200_particle_soa* particles);
@@ -177,6 +183,9 @@ int nb200_bank_free(nb200_particle_soa* particles);
 /* Raw device/host copies for hosts without a CUDA binding of their own. */
 int nb200_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes);
 int nb200_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes);
+/* Asynchronous flavours on a caller-supplied cudaStream_t (pinned host memory). */
+int nb200_memcpy_h2d_async(void* dst_device, const void* src_host, size_t bytes, void* cuda_stream);
+int nb200_memcpy_d2h_async(void* dst_host, const void* src_device, size_t bytes, void* cuda_stream);
 int nb200_memset_d(void* dst_device, int value, size_t bytes);
 int nb200_synchronize(void);
 

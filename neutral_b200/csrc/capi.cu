@@ -854,6 +854,38 @@ extern "C" int nb200_bank_upload(nb200_particle_soa* particles, const nb200_part
   return 0;
 }
 
+// The plain device SoA view behind the handle (allocated on first use). Together with
+// nb200_bank_import / nb200_bank_export it lets a host move banks with its own asynchronous
+// copies: fill the view, then import; export, then read the view.
+extern "C" int nb200_bank_view(nb200_particle_soa* particles, nb200_particle_soa* view_out) {
+  if (ensure_ready() != 0) return -1;
+  Bank* bank = bank_of(particles);
+  if (!bank || !view_out) {
+    set_error("nb200_bank_view: not a bank handle");
+    return -3;
+  }
+  if (!bank->has_export) {
+    soa_alloc(bank->exported, bank->n);
+    bank->has_export = true;
+    reinterpret_cast<BankHandle*>(particles)->view = as_public(bank->exported);
+  }
+  *view_out = as_public(bank->exported);
+  return 0;
+}
+
+// Rebuilds the bank from its plain SoA view (asynchronous on the library's stream).
+extern "C" int nb200_bank_import(nb200_particle_soa* particles) {
+  if (ensure_ready() != 0) return -1;
+  Bank* bank = bank_of(particles);
+  if (!bank || !bank->has_export) {
+    set_error("nb200_bank_import: not a bank handle, or its view was never requested");
+    return -3;
+  }
+  g.launches += launch_import_soa(bank->cur, bank->exported, bank->n, 0, g.stream);
+  bank->n_upper = bank->n;
+  return 0;
+}
+
 extern "C" int nb200_accumulate(double* dst_device, const double* src_device, size_t n) {
   if (ensure_ready() != 0) return -1;
   g.launches += launch_accumulate(dst_device, src_device, n, g.stream);
@@ -954,6 +986,22 @@ extern "C" int nb200_memcpy_d2h(void* dst_host, const void* src_device, size_t b
   if (ensure_ready() != 0) return -1;
   CU_TRY(cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, g.stream));
   CU_TRY(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+extern "C" int nb200_memcpy_h2d_async(void* dst_device, const void* src_host, size_t bytes,
+                                      void* cuda_stream) {
+  if (ensure_ready() != 0) return -1;
+  CU_TRY(cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice,
+                         (cudaStream_t)cuda_stream));
+  return 0;
+}
+
+extern "C" int nb200_memcpy_d2h_async(void* dst_host, const void* src_device, size_t bytes,
+                                      void* cuda_stream) {
+  if (ensure_ready() != 0) return -1;
+  CU_TRY(cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost,
+                         (cudaStream_t)cuda_stream));
   return 0;
 }
 

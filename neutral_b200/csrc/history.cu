@@ -50,6 +50,8 @@ enum : unsigned {
   kFlagSpeedOk = 1u,      // the speed is inside the proven range of div_by_known
   kFlagCellMfpOk = 2u,    // so is the cell mean free path
   kFlagDivOk = kFlagSpeedOk | kFlagCellMfpOk,
+  kFlagInvStale = 64u,    // the two reciprocals have not been recomputed since their divisors
+                          // changed: collision chains never need them, the next facet does
   kFlagCoarseMixed = 4u,  // the current coarse tile is not uniform: consult the fine map
   kFlagFineMixed = 8u,    // nor is the current 16x16 tile: densities come from the mesh
   kFlagAnyMixed = kFlagCoarseMixed | kFlagFineMixed,
@@ -81,8 +83,7 @@ __device__ __forceinline__ void derive(const StepArgs& a, double e, double nd, D
   Sig_s = S_s;
   p_absorb = S_a / S_t;
   d.cell_mfp = 1.0 / S_t;
-  d.cell_mfp_inv = 1.0 / d.cell_mfp;
-  flags = safe_exponent(d.cell_mfp) ? (flags | kFlagCellMfpOk) : (flags & ~kFlagCellMfpOk);
+  flags = (flags & ~kFlagCellMfpOk) | kFlagInvStale;  // cell_mfp_inv is recomputed on demand
 }
 
 // Direction of travel along one axis as a cell step: +1, -1, or 0 for a component that is
@@ -196,8 +197,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
     Derived d;
     derive(a, ew.x, nd, d, PARKED(Sig_s), PARKED(p_absorb), flags);
     double v = speed_of(ew.x);
-    double v_inv = 1.0 / v;
-    if (safe_exponent(v)) flags |= kFlagSpeedOk;
+    double v_inv = 0.0;  // recomputed on demand (kFlagInvStale is set)
     double uxi = 1.0 / (ox * v);
     double uyi = 1.0 / (oy * v);
     // ---- ... and the edges the particle is heading for (change when it crosses or turns)
@@ -226,6 +226,13 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
         double e_next = __ldg((x_facet ? a.edgex : a.edgey) + (reflect ? c : cn) + (up_next ? 1 : 0));
         nf++;
         double q_mfp, q_dtc;
+        if (kFastDiv && (flags & kFlagInvStale)) {  // first facet after a collision / new density
+          v_inv = 1.0 / v;
+          d.cell_mfp_inv = 1.0 / d.cell_mfp;
+          flags &= ~(kFlagInvStale | kFlagDivOk);
+          if (safe_exponent(v)) flags |= kFlagSpeedOk;
+          if (safe_exponent(d.cell_mfp)) flags |= kFlagCellMfpOk;
+        }
         if (kFastDiv && (flags & kFlagDivOk) == kFlagDivOk && safe_exponent(d_facet)) {
           q_mfp = div_by_known_unchecked(d_facet, d.cell_mfp, d.cell_mfp_inv);
           q_dtc = div_by_known_unchecked(d_facet, v, v_inv);
@@ -294,7 +301,13 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
             }
           }
         }
+#ifdef NB_EXPERIMENT_NO_COLLISION
       } else if (collide) {
+        break;  // experiment: how fast is a facet-only kernel (stream deck only)
+      } else if (false) {
+#else
+      } else if (collide) {
+#endif
         // ---- collision_event, :209-300
         nc++;
         const uint64_t pkey = a.pid0 + (uint64_t)(unsigned)PARKED(origin);
@@ -322,8 +335,9 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
           // already held, so nothing that depends on them needs recomputing.
         } else {
           const double mu = 1.0 - 2.0 * a1;
-          const double e_new = (e * ((kMassNo * kMassNo + (2.0 * kMassNo) * mu) + 1.0)) /
-                               ((kMassNo + 1.0) * (kMassNo + 1.0));
+          const double e_num = e * ((kMassNo * kMassNo + (2.0 * kMassNo) * mu) + 1.0);
+          const double e_new = kFastDiv ? NB_DIV_CONST(e_num, (kMassNo + 1.0) * (kMassNo + 1.0))
+                                        : e_num / ((kMassNo + 1.0) * (kMassNo + 1.0));
           const double ct = 0.5 * ((kMassNo + 1.0) * sqrt(e_new / e) -
                                    (kMassNo - 1.0) * sqrt(e / e_new));
           const double st = sqrt(1.0 - ct * ct);
@@ -333,9 +347,8 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
           oy = noy;
           PARKED(e) = e_new;
           derive(a, e_new, nd, d, PARKED(Sig_s), PARKED(p_absorb), flags);
-          v = speed_of(e_new);
-          v_inv = 1.0 / v;
-          flags = safe_exponent(v) ? (flags | kFlagSpeedOk) : (flags & ~kFlagSpeedOk);
+          v = kFastDiv ? speed_of_fast(e_new) : speed_of(e_new);
+          flags = (flags & ~kFlagSpeedOk) | kFlagInvStale;  // v_inv is recomputed on demand
           uxi = 1.0 / (ox * v);
           uyi = 1.0 / (oy * v);
           ex = target_edge(a.edgex, cx, axis_step(ox));

@@ -99,6 +99,15 @@ __device__ __forceinline__ double div_by_known(double a, double b, double y) {
   return a / b;
 }
 
+// Division by a compile-time constant through its (compile-time, correctly rounded)
+// reciprocal: the same IEEE quotient, ~5 FP64 operations instead of a full divide.
+#define NB_DIV_CONST(a, b) nb::div_by_known((a), (b), 1.0 / (b))
+
+// speed_of (nb_math.cuh; omp3/neutral.c:117,297) with the division by PARTICLE_MASS done that way.
+__device__ __forceinline__ double speed_of_fast(double e) {
+  return sqrt(NB_DIV_CONST((2.0 * e) * kEvToJ, kParticleMass));
+}
+
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

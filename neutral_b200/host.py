@@ -45,7 +45,8 @@ EXPORTED_SYMBOLS = [
     "nb200_abi_version", "nb200_last_error", "nb200_device_count", "nb200_set_stream",
     "nb200_set_shard", "nb200_bank_create", "nb200_bank_download", "nb200_bank_export",
     "nb200_bank_upload", "nb200_accumulate", "nb200_accumulate_clear", "nb200_bank_copy", "nb200_bank_size", "nb200_bank_free", "nb200_memcpy_h2d",
-    "nb200_memcpy_d2h", "nb200_memset_d", "nb200_synchronize", "nb200_set_option",
+    "nb200_memcpy_d2h", "nb200_memcpy_h2d_async", "nb200_memcpy_d2h_async", "nb200_bank_view",
+    "nb200_bank_import", "nb200_memset_d", "nb200_synchronize", "nb200_set_option",
     "nb200_last_step_stats", "nb200_kernel_launches", "nb200_selftest_rng_log",
     "nb200_selftest_log", "nb200_selftest_div", "nb200_selftest_cs", "nb200_host_threefry2x64_20",
     "nb200_host_log",
@@ -102,6 +103,10 @@ def load_library(build: bool = False) -> C.CDLL:
     L.nb200_bank_free.argtypes = [_soa_p]
     L.nb200_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.nb200_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.nb200_memcpy_h2d_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.nb200_memcpy_d2h_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.nb200_bank_view.argtypes = [_soa_p, _soa_p]
+    L.nb200_bank_import.argtypes = [_soa_p]
     L.nb200_memset_d.argtypes = [C.c_void_p, C.c_int, C.c_size_t]
     L.nb200_set_option.argtypes = [C.c_char_p, C.c_int]
     L.nb200_last_step_stats.argtypes = [_u64p]
