@@ -36,7 +36,26 @@ constexpr double kOpenBoundCorrection = 1.0e-13;
 // Written from the published algorithm; pinned by the known-answer vectors in
 // tests/test_kat.py.
 // ---------------------------------------------------------------------------------------
-NB_HD uint64_t rotl64(uint64_t v, int r) { return (v << r) | (v >> (64 - r)); }
+// 64-bit rotate by a compile-time amount. On the device it is spelled as two 32-bit funnel
+// shifts (SHF.L.W), or a plain register swap for r == 32: left to itself the compiler builds
+// each half from three shift/multiply/logic instructions.
+NB_HD uint64_t rotl64(uint64_t v, int r) {
+#if defined(__CUDA_ARCH__)
+  unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+  if (r >= 32) {
+    const unsigned t = lo;
+    lo = hi;
+    hi = t;
+    r -= 32;
+  }
+  if (r == 0) return ((uint64_t)hi << 32) | lo;
+  const unsigned nhi = __funnelshift_l(lo, hi, r);
+  const unsigned nlo = __funnelshift_l(hi, lo, r);
+  return ((uint64_t)nhi << 32) | nlo;
+#else
+  return (v << r) | (v >> (64 - r));
+#endif
+}
 
 #define NB_TF_ROUND(R)            \
   a += b;                         \
