@@ -194,6 +194,10 @@ int nb200_synchronize(void);
 int nb200_accumulate(double* dst_device, const double* src_device, size_t n);
 /* The same, and src[i] = 0 afterwards (the delta buffer is ready for its next timestep). */
 int nb200_accumulate_clear(double* dst_device, double* src_device, size_t n);
+/* The same on a caller-supplied cudaStream_t: lets a multi-GPU host fold a reduced delta
+ * into the tally beside the next timestep's transport (neutral_b200/multi.py). */
+int nb200_accumulate_clear_async(double* dst_device, double* src_device, size_t n,
+                                 void* cuda_stream);
 
 /* Options: "print" (1: print the reference's "Particles" line); "pipeline" (1, default:
  * phased timestep - begin-step/classify, counting sort by next-event type and tile, event
@@ -204,8 +208,15 @@ int nb200_accumulate_clear(double* dst_device, double* src_device, size_t n);
  * "tally_prereduce" (1: combine same-cell tally flushes of a warp with shuffles before the
  * atomic; default 0); "l2_persist" (1: the history kernel's launch carries an access-policy
  * window that keeps the staged cross-section tables persisting in L2; default 0).
+ * "defer_finish" (1: solve_transport_2d returns as soon as the timestep is enqueued on the
+ * stream; the counts are collected - and the reference's "Particles" line printed - by
+ * nb200_solve_finish, which must be called before the next solve_transport_2d; default 0).
  * Returns the previous value, or a negative code for an unknown name. */
 int nb200_set_option(const char* name, int value);
+/* Completes a timestep enqueued under defer_finish=1: waits for the stream and ADDS the
+ * step's counts to *facet_events / *collision_events (either may be null), like
+ * omp3/neutral.c:202-203. */
+int nb200_solve_finish(uint64_t* facet_events, uint64_t* collision_events);
 
 /* Statistics of the most recent solve_transport_2d: out[0..4] = facets, collisions,
  * particles processed, census events, deaths; out[5] = kernels launched by that call;

@@ -87,6 +87,9 @@ struct Context {
   int opt_length_bins = 512;
   int opt_tally_prereduce = 0;
   int opt_l2_persist = 0;
+  int opt_defer_finish = 0;
+  Bank* pending_bank = nullptr;  // a step enqueued by solve_transport_2d, not yet finished
+  uint64_t pending_launches0 = 0;
   bool l2_limit_set = false;
   // mesh extent, read once per (edgex, edgey) pair for the sort's history-length estimate
   const double* mesh_ex = nullptr;
@@ -344,12 +347,17 @@ void stage_tiles(StepArgs& a) {
                                    &a.tiles, g.stream);
 }
 
+void finish_step(uint64_t* facet_events, uint64_t* collision_events);
+
 // The one timestep both flavours share. All pointers are device memory.
 void run_step(Bank* bank, int nx, int ny, uint64_t master_key, double dt, int ntotal,
               const double* density, const double* edgex, const double* edgey,
               const double* s_keys, const double* s_vals, int s_n, const double* a_keys,
               const double* a_vals, int a_n, double* tally, uint64_t* r0, uint64_t* r1,
               uint64_t* r2, uint64_t* facet_events, uint64_t* collision_events) {
+  if (g.pending_bank)
+    terminate("solve_transport_2d: the previous timestep was enqueued with defer_finish=1 and "
+              "nb200_solve_finish has not been called");
   const uint64_t launches0 = g.launches;
   StepArgs a{};
   a.nx = nx;
@@ -444,6 +452,20 @@ void run_step(Bank* bank, int nx, int ny, uint64_t master_key, double dt, int nt
   CU_FATAL(cudaEventRecord(g.ev_end, g.stream));
   CU_FATAL(cudaMemcpyAsync(g.h_totals, g.d_totals, sizeof(unsigned long long) * kTotCount,
                            cudaMemcpyDeviceToHost, g.stream));
+  g.pending_bank = bank;
+  g.pending_launches0 = launches0;
+  // "defer_finish": the caller overlaps its own host work (launching the collective that
+  // combines this step's tally delta, say) with the step and collects the counts later
+  if (!g.opt_defer_finish) finish_step(facet_events, collision_events);
+}
+
+// Second half of a timestep: waits for the stream, checks the device-side faults, updates
+// the live-prefix bound and hands the counts to the caller (omp3/neutral.c:202-205).
+void finish_step(uint64_t* facet_events, uint64_t* collision_events) {
+  Bank* bank = g.pending_bank;
+  if (!bank) return;
+  g.pending_bank = nullptr;
+  const uint64_t launches0 = g.pending_launches0;
   CU_FATAL(cudaStreamSynchronize(g.stream));
   if (g.h_totals[kTotFault])
     terminate("solve_transport_2d: the cross-section tables are not what they were when first "
@@ -764,6 +786,7 @@ extern "C" void nb200_solve_transport_2d_host(
   run_step(&bank, nx, ny, master_key, dt, ntotal_particles, d_density, d_edgex, d_edgey, d_sk,
            d_sv, s_n, d_ak, d_av, a_n, d_tally, d_r[0], d_r[1], d_r[2], facet_events,
            collision_events);
+  finish_step(facet_events, collision_events);  // the host flavour never defers (no-op if done)
   g.cs_s_keys = nullptr;
   g.launches += launch_export_aos(bank.cur, d_aos, n, g.stream);
   CU_FATAL(cudaMemcpyAsync(particles, d_aos, sizeof(nb200_particle_aos) * (size_t)n,
@@ -898,6 +921,13 @@ extern "C" int nb200_accumulate_clear(double* dst_device, double* src_device, si
   return 0;
 }
 
+extern "C" int nb200_accumulate_clear_async(double* dst_device, double* src_device, size_t n,
+                                            void* cuda_stream) {
+  if (ensure_ready() != 0) return -1;
+  g.launches += launch_accumulate_clear(dst_device, src_device, n, (cudaStream_t)cuda_stream);
+  return 0;
+}
+
 extern "C" int nb200_bank_export(nb200_particle_soa* particles) {
   if (ensure_ready() != 0) return -1;
   Bank* bank = bank_of(particles);
@@ -1026,6 +1056,7 @@ extern "C" int nb200_set_option(const char* name, int value) {
   else if (strcmp(name, "length_bins") == 0) slot = &g.opt_length_bins;
   else if (strcmp(name, "tally_prereduce") == 0) slot = &g.opt_tally_prereduce;
   else if (strcmp(name, "l2_persist") == 0) slot = &g.opt_l2_persist;
+  else if (strcmp(name, "defer_finish") == 0) slot = &g.opt_defer_finish;
   if (!slot) {
     set_error("nb200_set_option: unknown option '%s'", name);
     return -3;
@@ -1033,6 +1064,18 @@ extern "C" int nb200_set_option(const char* name, int value) {
   const int prev = *slot;
   *slot = value;
   return prev;
+}
+
+extern "C" int nb200_solve_finish(uint64_t* facet_events, uint64_t* collision_events) {
+  if (!g.pending_bank) {
+    set_error("nb200_solve_finish: no timestep is pending");
+    return -3;
+  }
+  uint64_t f = 0, c = 0;
+  finish_step(&f, &c);
+  if (facet_events) *facet_events += f;
+  if (collision_events) *collision_events += c;
+  return 0;
 }
 
 extern "C" int nb200_last_step_stats(uint64_t out[8]) {

@@ -44,10 +44,10 @@ EXPORTED_SYMBOLS = [
     "nb200_solve_transport_2d_host",
     "nb200_abi_version", "nb200_last_error", "nb200_device_count", "nb200_set_stream",
     "nb200_set_shard", "nb200_bank_create", "nb200_bank_download", "nb200_bank_export",
-    "nb200_bank_upload", "nb200_accumulate", "nb200_accumulate_clear", "nb200_bank_copy", "nb200_bank_size", "nb200_bank_free", "nb200_memcpy_h2d",
+    "nb200_bank_upload", "nb200_accumulate", "nb200_accumulate_clear", "nb200_accumulate_clear_async", "nb200_bank_copy", "nb200_bank_size", "nb200_bank_free", "nb200_memcpy_h2d",
     "nb200_memcpy_d2h", "nb200_memcpy_h2d_async", "nb200_memcpy_d2h_async", "nb200_bank_view",
     "nb200_bank_import", "nb200_memset_d", "nb200_synchronize", "nb200_set_option",
-    "nb200_last_step_stats", "nb200_kernel_launches", "nb200_selftest_rng_log",
+    "nb200_solve_finish", "nb200_last_step_stats", "nb200_kernel_launches", "nb200_selftest_rng_log",
     "nb200_selftest_log", "nb200_selftest_div", "nb200_selftest_cs", "nb200_host_threefry2x64_20",
     "nb200_host_log",
 ]
@@ -98,6 +98,7 @@ def load_library(build: bool = False) -> C.CDLL:
     L.nb200_bank_upload.argtypes = [_soa_p, _soa_p]
     L.nb200_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.nb200_accumulate_clear.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.nb200_accumulate_clear_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.nb200_bank_copy.argtypes = [_soa_p, _soa_p]
     L.nb200_bank_size.argtypes = [_soa_p]
     L.nb200_bank_free.argtypes = [_soa_p]
@@ -110,6 +111,7 @@ def load_library(build: bool = False) -> C.CDLL:
     L.nb200_memset_d.argtypes = [C.c_void_p, C.c_int, C.c_size_t]
     L.nb200_set_option.argtypes = [C.c_char_p, C.c_int]
     L.nb200_last_step_stats.argtypes = [_u64p]
+    L.nb200_solve_finish.argtypes = [_u64p, _u64p]
     L.nb200_kernel_launches.restype = C.c_uint64
     L.nb200_selftest_rng_log.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, _u64p,
                                          _dp, _dp]
@@ -263,9 +265,14 @@ class Simulation:
         return host
 
     # -- stepping -----------------------------------------------------------------------
-    def step(self, tt: int, tally_ptr: Optional[int] = None) -> StepResult:
-        """One call of ``solve_transport_2d`` with ``master_key = tt`` (``main.c:101-110``)."""
+    def step(self, tt: int, tally_ptr: Optional[int] = None, defer: bool = False
+             ) -> Optional[StepResult]:
+        """One call of ``solve_transport_2d`` with ``master_key = tt`` (``main.c:101-110``).
+        ``defer=True`` returns as soon as the timestep is enqueued (library option
+        ``defer_finish``); :meth:`step_finish` then waits for it and returns the counts."""
         d = self.problem.deck
+        if defer:
+            self.lib.nb200_set_option(b"defer_finish", 1)
         nlocal = C.c_int(self.count)
         facets, colls = C.c_uint64(0), C.c_uint64(0)
         ctr = [c.ptr for c in self.counters] if self.counters else [None] * 3
@@ -275,9 +282,21 @@ class Simulation:
             None, None, C.byref(self.cs[0]), C.byref(self.cs[1]),
             tally_ptr if tally_ptr is not None else self.tally.ptr,
             ctr[0], ctr[1], ctr[2], C.byref(facets), C.byref(colls))
+        if defer:
+            return None
+        return self._result(facets.value, colls.value)
+
+    def step_finish(self) -> StepResult:
+        """Completes a ``step(..., defer=True)``: waits for the timestep and returns its counts."""
+        facets, colls = C.c_uint64(0), C.c_uint64(0)
+        _check(self.lib.nb200_solve_finish(C.byref(facets), C.byref(colls)), "solve_finish")
+        self.lib.nb200_set_option(b"defer_finish", 0)
+        return self._result(facets.value, colls.value)
+
+    def _result(self, facets: int, colls: int) -> StepResult:
         stats = (C.c_uint64 * 8)()
         self.lib.nb200_last_step_stats(stats)
-        assert stats[0] == facets.value and stats[1] == colls.value
+        assert stats[0] == facets and stats[1] == colls
         return StepResult(int(stats[0]), int(stats[1]), int(stats[2]), int(stats[3]),
                           int(stats[4]), int(stats[5]), int(stats[6]), int(stats[7]))
 

@@ -11,8 +11,12 @@ output is the additive energy-deposition tally, which is CUMULATIVE across times
     all_reduce(delta, SUM)                                           # one collective per step
     tally  += delta                                                  # every rank
 
-The all-reduce of timestep ``t`` overlaps the transport of timestep ``t+1`` (two delta buffers):
-it is launched asynchronously and only waited for when its buffer is needed again.
+The all-reduce of timestep ``t`` overlaps the transport of timestep ``t+1``: it is launched
+asynchronously and its buffer is only folded into the tally when the buffer is needed again.
+An engine with three delta buffers and a side stream (:class:`GpuShardEngine`) also takes the
+fold itself off the critical path: ``tally += delta; delta = 0`` is queued behind the
+all-reduce on the side stream and runs beside the next transport, which deposits into the
+third buffer.
 
 The loop is written against a small engine protocol so that the same code drives the CUDA
 path (``bench.py``: :class:`GpuShardEngine`, NCCL) and, in the CPU tests, the oracle over
@@ -38,7 +42,12 @@ class StepCounts:
 
 
 class ShardEngine(Protocol):
-    """What one rank must provide. ``k`` selects one of two delta buffers."""
+    """What one rank must provide. ``k`` selects one of ``nbuffers`` delta buffers (attribute,
+    default 2). An engine that can fold asynchronously also provides ``fold_async(k, work)``
+    (queue "wait for ``work``, tally += delta[k], delta[k] = 0" without blocking the host;
+    with ``step_begin(tt, k)`` / ``step_end()`` the timestep itself is only enqueued first, so
+    the collective is launched while the transport runs), ``acquire(k)`` (order the next use of buffer ``k`` behind its queued fold) and ``drain()``
+    (order everything that follows behind all queued folds)."""
 
     def step_into_delta(self, tt: int, k: int):
         """One ``solve_transport_2d`` (master_key = tt) of this rank's shard, depositing into
@@ -56,24 +65,42 @@ def run_timesteps(engine: ShardEngine, iterations: int, world: int, dist=None,
     """Runs ``iterations`` timesteps of a sharded problem; returns the per-step counts of THIS
     rank. ``dist`` is ``torch.distributed`` (initialised) when ``world > 1``."""
     out = []
-    pending = None  # (work handle, buffer index) of the all-reduce still in flight
-    for i in range(iterations):
-        tt = first_tt + i
-        k = i & 1
-        out.append(engine.step_into_delta(tt, k))
-        if pending is not None:  # timestep tt-1's reduction overlapped this transport
-            work, kp = pending
+    nbuf = getattr(engine, "nbuffers", 2)
+    async_fold = overlap and world > 1 and hasattr(engine, "fold_async")
+    pending = []  # (step index, buffer, work handle): reductions in flight, fold still owed
+
+    def fold_through(last_index: int) -> None:
+        while pending and pending[0][0] <= last_index:
+            _, kp, work = pending.pop(0)
             if work is not None:
                 work.wait()
             engine.accumulate_and_clear(kp)
-            pending = None
-        if world > 1:
-            work = dist.all_reduce(engine.delta_tensor(k), async_op=True)
-            if overlap and i + 1 < iterations:
-                pending = (work, k)
-                continue
-            work.wait()
-        engine.accumulate_and_clear(k)
+
+    for i in range(iterations):
+        k = i % nbuf
+        fold_through(i - nbuf)  # buffer k is about to be deposited into again
+        if async_fold:
+            engine.acquire(k)
+        if async_fold and hasattr(engine, "step_begin"):
+            # the collective and the fold are queued behind the transport while it runs, so
+            # their launch latency is off the critical path too
+            engine.step_begin(first_tt + i, k)
+            engine.fold_async(k, dist.all_reduce(engine.delta_tensor(k), async_op=True))
+            out.append(engine.step_end())
+            continue
+        out.append(engine.step_into_delta(first_tt + i, k))
+        work = dist.all_reduce(engine.delta_tensor(k), async_op=True) if world > 1 else None
+        if async_fold:
+            engine.fold_async(k, work)
+        elif overlap and world > 1:
+            fold_through(i - 1)  # the previous reduction overlapped this transport
+            pending.append((i, k, work))
+        else:
+            pending.append((i, k, work))
+            fold_through(i)
+    fold_through(iterations)
+    if async_fold:
+        engine.drain()
     return out
 
 
@@ -88,23 +115,57 @@ def global_counts(local: List, world: int, dist=None, device=None):
 
 
 class GpuShardEngine:
-    """The CUDA path: a :class:`neutral_b200.host.Simulation` plus two device delta buffers."""
+    """The CUDA path: a :class:`neutral_b200.host.Simulation`, three device delta buffers and a
+    side stream on which reduced deltas are folded into the tally."""
+
+    nbuffers = 3
 
     def __init__(self, sim, ncells: int):
         import torch
+        self.torch = torch
         self.sim = sim
         self.lib = sim.lib
         self.ncells = ncells
-        self.delta = [torch.zeros(ncells, dtype=torch.float64, device="cuda") for _ in range(2)]
+        self.delta = [torch.zeros(ncells, dtype=torch.float64, device="cuda")
+                      for _ in range(self.nbuffers)]
+        self.side = torch.cuda.Stream()
+        self.folded = [torch.cuda.Event() for _ in range(self.nbuffers)]
 
     def step_into_delta(self, tt: int, k: int):
         return self.sim.step(tt, tally_ptr=self.delta[k].data_ptr())
 
+    def step_begin(self, tt: int, k: int) -> None:
+        """Enqueues the timestep and returns (``Simulation.step(defer=True)``)."""
+        self.sim.step(tt, tally_ptr=self.delta[k].data_ptr(), defer=True)
+
+    def step_end(self):
+        return self.sim.step_finish()
+
     def delta_tensor(self, k: int):
         return self.delta[k]
 
-    def accumulate_and_clear(self, k: int) -> None:
-        rc = self.lib.nb200_accumulate_clear(self.sim.tally.ptr, self.delta[k].data_ptr(),
-                                             self.ncells)
+    def _check(self, rc: int) -> None:
         if rc != 0:
             raise RuntimeError(self.lib.nb200_last_error().decode())
+
+    def accumulate_and_clear(self, k: int) -> None:
+        self._check(self.lib.nb200_accumulate_clear(self.sim.tally.ptr, self.delta[k].data_ptr(),
+                                                    self.ncells))
+
+    def fold_async(self, k: int, work) -> None:
+        torch = self.torch
+        if work is None:  # no collective in front: order the fold behind the transport itself
+            self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            if work is not None:
+                work.wait()  # the side stream waits for the collective, the host does not
+            self._check(self.lib.nb200_accumulate_clear_async(
+                self.sim.tally.ptr, self.delta[k].data_ptr(), self.ncells,
+                self.side.cuda_stream))
+            self.folded[k].record(self.side)
+
+    def acquire(self, k: int) -> None:
+        self.torch.cuda.current_stream().wait_event(self.folded[k])
+
+    def drain(self) -> None:
+        self.torch.cuda.current_stream().wait_stream(self.side)

@@ -173,3 +173,35 @@ def test_edge_cases(gpu_lib, port):
     assert (r.facets, r.collisions, r.processed) == (pf, pc, pp)
     assert sum(sim.bank_to_host().bit_equal(bank).values()) == 0
     sim.free()
+
+
+def test_deferred_step_and_async_fold(gpu_lib, port):
+    """solve_transport_2d under defer_finish + nb200_solve_finish, and the multi-GPU engine's
+    three-buffer / side-stream fold, give the single-call result: exact counts, bit-equal
+    bank, tally within tolerance (the fold only changes the summation order)."""
+    import torch
+    from neutral_b200.multi import GpuShardEngine
+
+    prob = build_problem("csp_small")
+    d = prob.deck
+    bank = port.inject(prob)
+    tally = np.zeros(d.nx * d.ny)
+    want = [port.step(prob, bank, tt, tally) for tt in range(1, d.iterations + 1)]
+    sim = Simulation(prob, per_particle_counters=False)
+    sim.inject()
+    eng = GpuShardEngine(sim, d.nx * d.ny)
+    got = []
+    for i in range(d.iterations):
+        k = i % eng.nbuffers
+        eng.acquire(k)
+        eng.step_begin(i + 1, k)
+        eng.fold_async(k, None)  # queued behind the transport on the side stream
+        r = eng.step_end()
+        got.append((r.facets, r.collisions, r.processed))
+    eng.drain()
+    torch.cuda.synchronize()
+    assert got == want
+    assert sum(sim.bank_to_host().bit_equal(bank).values()) == 0
+    assert tally_close(sim.tally_to_host(), tally)
+    assert all(not bool(t.any()) for t in eng.delta), "delta buffers must end up cleared"
+    sim.free()

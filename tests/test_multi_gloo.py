@@ -35,7 +35,8 @@ class OracleShardEngine:
         self.pid0, self.count = shard_range(d.nparticles, rank, world)
         self.bank = self.port.inject(prob, self.pid0, self.count)
         self.tally = np.zeros(d.nx * d.ny)
-        self.delta = [torch.zeros(d.nx * d.ny, dtype=torch.float64) for _ in range(2)]
+        self.delta = [torch.zeros(d.nx * d.ny, dtype=torch.float64)
+                      for _ in range(getattr(self, "nbuffers", 2))]
 
     def step_into_delta(self, tt, k):
         assert not self.delta[k].any(), "delta buffer must be clear on entry"
@@ -53,19 +54,66 @@ class OracleShardEngine:
         self.delta[k].zero_()
 
 
+class AsyncOracleShardEngine(OracleShardEngine):
+    """The protocol of the CUDA engine (three buffers, folds queued behind the collective and
+    taken off the loop's critical path), with the queue drained lazily on the host."""
+
+    nbuffers = 3
+
+    def __init__(self, prob, rank, world):
+        super().__init__(prob, rank, world)
+        self.queue = []
+        self.max_queued = 0
+
+    def step_begin(self, tt, k):
+        self._begun = (tt, k)
+
+    def step_end(self):
+        # the collective of this step was launched before its transport "finished": run the
+        # transport now and make the queued fold wait for a reduction of the finished delta
+        tt, k = self._begun
+        counts = self.step_into_delta(tt, k)
+        kq, _ = self.queue.pop()
+        assert kq == k
+        self.queue.append((k, dist.all_reduce(self.delta[k], async_op=True)))
+        return counts
+
+    def fold_async(self, k, work):
+        if work is not None and hasattr(self, "_begun") and self._begun[1] == k:
+            work.wait()  # a reduction of the still-empty buffer: harmless, discarded
+        self.queue.append((k, work))
+        self.max_queued = max(self.max_queued, len(self.queue))
+
+    def _run(self, n):
+        for k, work in self.queue[:n]:
+            work.wait()
+            self.accumulate_and_clear(k)
+        del self.queue[:n]
+
+    def acquire(self, k):
+        ks = [q[0] for q in self.queue]
+        if k in ks:
+            self._run(ks.index(k) + 1)
+
+    def drain(self):
+        self._run(len(self.queue))
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, deck, overlap, out):
+def _worker(rank, world, port, deck, overlap, out, async_fold=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         prob = build_problem(deck)
-        eng = OracleShardEngine(prob, rank, world)
+        eng = (AsyncOracleShardEngine if async_fold else OracleShardEngine)(prob, rank, world)
         local = run_timesteps(eng, prob.deck.iterations, world, dist, overlap=overlap)
+        if async_fold:
+            assert not eng.queue and eng.max_queued >= min(2, prob.deck.iterations)
         total = global_counts(local, world, dist)
         # every rank must hold the same cumulative tally
         t = torch.from_numpy(eng.tally.copy())
@@ -81,11 +129,12 @@ def _worker(rank, world, port, deck, overlap, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,deck,overlap", [(2, "mixed_small", True), (2, "csp_small", False),
-                                                (3, "split_small", True)])
-def test_sharded_timesteps_over_gloo(tmp_path, port, world, deck, overlap):
-    mp.spawn(_worker, args=(world, _free_port(), deck, overlap, str(tmp_path)), nprocs=world,
-             join=True)
+@pytest.mark.parametrize("world,deck,overlap,async_fold",
+                         [(2, "mixed_small", True, False), (2, "csp_small", False, False),
+                          (3, "split_small", True, False), (2, "csp_small", True, True)])
+def test_sharded_timesteps_over_gloo(tmp_path, port, world, deck, overlap, async_fold):
+    mp.spawn(_worker, args=(world, _free_port(), deck, overlap, str(tmp_path), async_fold),
+             nprocs=world, join=True)
     prob = build_problem(deck)
     d = prob.deck
     bank = port.inject(prob)
