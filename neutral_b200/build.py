@@ -17,7 +17,8 @@ CSRC = os.path.join(HERE, "csrc")
 # (e.g. NB200_DEFINES=-DNB_HISTORY_MIN_BLOCKS=5 NB200_LIB=libneutral_b200.mb5.so).
 LIB = os.path.join(HERE, os.environ.get("NB200_LIB", "libneutral_b200.so"))
 SOURCES = ["transport.cu", "stage.cu", "pipeline.cu", "history.cu", "capi.cu"]
-HEADERS = ["transport.cuh", "nb_device.cuh", "nb_bank.cuh", "nb_math.cuh", "glibc_log_table.inc",
+HEADERS = ["transport.cuh", "nb_device.cuh", "nb_bank.cuh", "nb_math.cuh", "nb_history.cuh",
+           "glibc_log_table.inc",
            os.path.join("..", "..", "include", "neutral_b200.h")]
 
 NVCC_FLAGS = [
