@@ -208,6 +208,8 @@ int nb200_accumulate_clear_async(double* dst_device, double* src_device, size_t 
  * "tally_prereduce" (1: combine same-cell tally flushes of a warp with shuffles before the
  * atomic; default 0); "l2_persist" (1: the history kernel's launch carries an access-policy
  * window that keeps the staged cross-section tables persisting in L2; default 0).
+ * "device_inject" (1, default: inject_particles generates the bank on the device with the
+ * bit-exact sin/cos of nb_sincos.cuh; 0: on the host with libm, then uploads it);
  * "defer_finish" (1: solve_transport_2d returns as soon as the timestep is enqueued on the
  * stream; the counts are collected - and the reference's "Particles" line printed - by
  * nb200_solve_finish, which must be called before the next solve_transport_2d; default 0).
@@ -242,6 +244,15 @@ int nb200_selftest_cs(const double* keys_host, const double* values_host, int ne
 void nb200_host_threefry2x64_20(uint64_t c0, uint64_t c1, uint64_t k0, uint64_t k1,
                                 uint64_t out[2]);
 double nb200_host_log(double x);
+/* sin/cos as inject_particles needs them: a transliteration of glibc's __sin_fma/__cos_fma
+ * (nb_sincos.cuh). Device evaluation of n host arguments; host builds of the same source;
+ * and a sweep that counts the arguments on which the host build and this process's libm
+ * differ in any bit (first offender in *bad_x). */
+int nb200_selftest_sincos(const double* x_host, double* sin_host, double* cos_host, int n);
+double nb200_host_sin(double x);
+double nb200_host_cos(double x);
+void nb200_host_sincos(const double* x, long long n, double* sin_out, double* cos_out);
+long long nb200_selftest_host_sincos(const double* x, long long n, double* bad_x);
 
 #ifdef __cplusplus
 }

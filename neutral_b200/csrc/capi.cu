@@ -17,10 +17,15 @@
 #include <vector>
 
 #include "transport.cuh"
+#include "nb_sincos.cuh"
 
 namespace {
 
 using namespace nb;
+
+const SinCosTable kHostSinCosTable = {{
+#include "glibc_sincos_table.inc"
+}};
 
 const LogTable kHostLogTable = {
 #include "glibc_log_table.inc"
@@ -76,6 +81,8 @@ struct Context {
   int device = 0;
   cudaStream_t stream = 0;
   LogTable* d_logt = nullptr;
+  SinCosTable* d_sct = nullptr;
+  int opt_device_inject = 1;
   unsigned long long* d_totals = nullptr;
   unsigned long long* h_totals = nullptr;  // pinned
   cudaEvent_t ev_begin = nullptr, ev_mid = nullptr, ev_end = nullptr;  // phase timing
@@ -171,6 +178,8 @@ int ensure_ready() {
   CU_TRY(cudaGetDevice(&g.device));
   CU_TRY(cudaMalloc(&g.d_logt, sizeof(LogTable)));
   CU_TRY(cudaMemcpy(g.d_logt, &kHostLogTable, sizeof(LogTable), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMalloc(&g.d_sct, sizeof(SinCosTable)));
+  CU_TRY(cudaMemcpy(g.d_sct, &kHostSinCosTable, sizeof(SinCosTable), cudaMemcpyHostToDevice));
   CU_TRY(cudaMalloc(&g.d_totals, sizeof(unsigned long long) * kTotCount));
   CU_TRY(cudaMallocHost(&g.h_totals, sizeof(unsigned long long) * kTotCount));
   CU_TRY(cudaEventCreate(&g.ev_begin));
@@ -600,6 +609,21 @@ extern "C" size_t inject_particles(
     terminate("inject_particles: shard [%d, %d) outside [0, %d)", first, first + count,
               nparticles);
 
+  if (g.opt_device_inject) {
+    // The bank is generated where it lives: no host loop, no 80-byte-per-particle upload.
+    size_t bytes = 0;
+    BankHandle* h = new_handle(count, (uint64_t)first, &bytes);
+    InjectArgs ia{edgex, edgey, local_nx, local_ny, local_particle_left_off,
+                  local_particle_bottom_off, local_particle_width, local_particle_height, dt,
+                  initial_energy};
+    g.launches += launch_inject(h->impl->cur, count, (uint64_t)first, ia, g.d_sct, g.stream);
+    CU_FATAL(cudaGetLastError());
+    CU_FATAL(cudaStreamSynchronize(g.stream));
+    *particles = &h->view;
+    return bytes;
+  }
+
+  // Host flavour ("device_inject" = 0): the same arithmetic with the host's libm.
   // The mesh edges live in kernel-set (device) memory.
   std::vector<double> ex(local_nx + 1), ey(local_ny + 1);
   CU_FATAL(cudaMemcpy(ex.data(), edgex, sizeof(double) * (local_nx + 1),
@@ -1057,6 +1081,7 @@ extern "C" int nb200_set_option(const char* name, int value) {
   else if (strcmp(name, "tally_prereduce") == 0) slot = &g.opt_tally_prereduce;
   else if (strcmp(name, "l2_persist") == 0) slot = &g.opt_l2_persist;
   else if (strcmp(name, "defer_finish") == 0) slot = &g.opt_defer_finish;
+  else if (strcmp(name, "device_inject") == 0) slot = &g.opt_device_inject;
   if (!slot) {
     set_error("nb200_set_option: unknown option '%s'", name);
     return -3;
@@ -1174,3 +1199,55 @@ extern "C" void nb200_host_threefry2x64_20(uint64_t c0, uint64_t c1, uint64_t k0
 }
 
 extern "C" double nb200_host_log(double x) { return nb_log(x, &kHostLogTable); }
+extern "C" double nb200_host_sin(double x) { return nb_sin(x, &kHostSinCosTable); }
+extern "C" double nb200_host_cos(double x) { return nb_cos(x, &kHostSinCosTable); }
+
+// Batch flavour of the two hooks above (the host build of the device source).
+extern "C" void nb200_host_sincos(const double* x, long long n, double* s, double* c) {
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < n; ++i) {
+    s[i] = nb_sin(x[i], &kHostSinCosTable);
+    c[i] = nb_cos(x[i], &kHostSinCosTable);
+  }
+}
+
+// Compares the host build of nb_sin/nb_cos with this process's libm on n arguments; returns
+// the number of arguments where either differs in any bit (first offender in *bad_x).
+extern "C" long long nb200_selftest_host_sincos(const double* x, long long n, double* bad_x) {
+  long long bad = 0;
+  double first_bad = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+  for (long long i = 0; i < n; ++i) {
+    const double s = nb_sin(x[i], &kHostSinCosTable), c = nb_cos(x[i], &kHostSinCosTable);
+    const double rs = sin(x[i]), rc = cos(x[i]);
+    if (memcmp(&s, &rs, 8) != 0 || memcmp(&c, &rc, 8) != 0) {
+      if (!bad) {
+#pragma omp critical
+        first_bad = x[i];
+      }
+      bad++;
+    }
+  }
+  if (bad_x) *bad_x = first_bad;
+  return bad;
+}
+
+// sin and cos of n host arguments, evaluated on the device.
+extern "C" int nb200_selftest_sincos(const double* x_host, double* s_host, double* c_host,
+                                     int n) {
+  if (ensure_ready() != 0) return -1;
+  double *d_x = nullptr, *d_s = nullptr, *d_c = nullptr;
+  CU_TRY(cudaMalloc(&d_x, sizeof(double) * n));
+  CU_TRY(cudaMalloc(&d_s, sizeof(double) * n));
+  CU_TRY(cudaMalloc(&d_c, sizeof(double) * n));
+  CU_TRY(cudaMemcpy(d_x, x_host, sizeof(double) * n, cudaMemcpyHostToDevice));
+  g.launches += launch_selftest_sincos(d_x, d_s, d_c, n, g.d_sct, g.stream);
+  CU_TRY(cudaStreamSynchronize(g.stream));
+  CU_TRY(cudaMemcpy(s_host, d_s, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(c_host, d_c, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  cudaFree(d_x);
+  cudaFree(d_s);
+  cudaFree(d_c);
+  return 0;
+}
+

@@ -12,6 +12,7 @@
 //  so that every particle field replays bit-identically.
 #include "transport.cuh"
 #include "nb_device.cuh"
+#include "nb_sincos.cuh"
 
 namespace nb {
 
@@ -162,6 +163,54 @@ __global__ void __launch_bounds__(kHistoryThreads) k_history_direct(const StepAr
   }
 
   flush_totals(a.totals, nf, nc, np, nz, nd_);
+}
+
+// --------------------------------------------------------------------------------------
+// k_inject: inject_particles (omp3/neutral.c:560-630) on the device, straight into the packed
+// bank. Particle kk of the global bank draws its position from Threefry(ctr={0,0},
+// key={kk,0}) (:581-584) and its angle from ctr={1,0} (:611-614); cos/sin replay glibc's
+// operation sequence (nb_sincos.cuh), so the bank equals the host-injected one bit for bit.
+// --------------------------------------------------------------------------------------
+
+// First cell whose half-open interval [edge[c], edge[c+1]) holds v; 0 when there is none -
+// what the reference's linear scan over the cells leaves behind (:590-603), by bisection.
+__device__ __forceinline__ int locate_cell(const double* __restrict__ edge, int ncells,
+                                           double v) {
+  if (!(v >= __ldg(edge))) return 0;
+  int lo = 0, hi = ncells;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (v >= __ldg(edge + mid)) lo = mid; else hi = mid;
+  }
+  return (v >= __ldg(edge + lo) && v < __ldg(edge + lo + 1)) ? lo : 0;
+}
+
+__global__ void __launch_bounds__(256) k_inject(BankView b, int count, uint64_t first,
+                                                InjectArgs ia, const SinCosTable* sct) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= count) return;
+  const uint64_t kk = first + (uint64_t)s;
+  double r0, r1;
+  random_pair(kk, 0, 0, r0, r1);
+  const double x = ia.left + r0 * ia.width;
+  const double y = ia.bottom + r1 * ia.height;
+  const int cx = locate_cell(ia.edgex, ia.nx, x);
+  const int cy = locate_cell(ia.edgey, ia.ny, y);
+  random_pair(kk, 0, 1, r0, r1);
+  const double theta = 2.0 * 3.14159265358979323846 * r0;
+  b.pos[s] = make_double2(x, y);
+  b.dir[s] = make_double2(nb_cos(theta, sct), nb_sin(theta, sct));
+  b.ew[s] = make_double2(ia.initial_energy, 1.0);
+  b.tm[s] = make_double2(ia.dt, 0.0);
+  b.meta[s] = make_int4(cx, cy, 0, s);
+}
+
+__global__ void k_selftest_sincos(const double* x, double* s, double* c, int n,
+                                  const SinCosTable* sct) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  s[i] = nb_sin(x[i], sct);
+  c[i] = nb_cos(x[i], sct);
 }
 
 // --------------------------------------------------------------------------------------
@@ -333,6 +382,19 @@ int launch_import_aos(BankView b, const void* aos, int n, cudaStream_t st) {
 int launch_export_aos(BankView b, void* aos, int n, cudaStream_t st) {
   if (n <= 0) return 0;
   k_export_aos<<<blocks_for(n, 256), 256, 0, st>>>(b, (AosParticle*)aos, n);
+  return 1;
+}
+
+int launch_inject(BankView b, int count, uint64_t first, const InjectArgs& ia,
+                  const SinCosTable* sct, cudaStream_t st) {
+  if (count <= 0) return 0;
+  k_inject<<<(count + 255) / 256, 256, 0, st>>>(b, count, first, ia, sct);
+  return 1;
+}
+
+int launch_selftest_sincos(const double* x, double* s, double* c, int n, const SinCosTable* sct,
+                           cudaStream_t st) {
+  k_selftest_sincos<<<(n + 255) / 256, 256, 0, st>>>(x, s, c, n, sct);
   return 1;
 }
 

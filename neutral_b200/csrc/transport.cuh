@@ -26,6 +26,20 @@ int launch_stage_tiles(const double* density, int nx, int ny, double* fine, doub
 int launch_selftest_div(const double* a, const double* b, double* fast, double* ieee, int n,
                         cudaStream_t st);
 
+// inject_particles on the device (transport.cu: k_inject). Edges are device pointers.
+struct SinCosTable;
+struct InjectArgs {
+  const double* edgex;
+  const double* edgey;
+  int nx, ny;
+  double left, bottom, width, height;  // the source box of neutral_data.c:39-95
+  double dt, initial_energy;
+};
+int launch_inject(BankView b, int count, uint64_t first, const InjectArgs& ia,
+                  const SinCosTable* sct, cudaStream_t st);
+int launch_selftest_sincos(const double* x, double* s, double* c, int n, const SinCosTable* sct,
+                           cudaStream_t st);
+
 int launch_import_soa(BankView b, SoaView s, int n, int origin0, cudaStream_t st);
 int launch_export_soa(BankView b, SoaView s, int n, cudaStream_t st);
 int launch_import_aos(BankView b, const void* aos, int n, cudaStream_t st);

@@ -49,7 +49,8 @@ EXPORTED_SYMBOLS = [
     "nb200_bank_import", "nb200_memset_d", "nb200_synchronize", "nb200_set_option",
     "nb200_solve_finish", "nb200_last_step_stats", "nb200_kernel_launches", "nb200_selftest_rng_log",
     "nb200_selftest_log", "nb200_selftest_div", "nb200_selftest_cs", "nb200_host_threefry2x64_20",
-    "nb200_host_log",
+    "nb200_host_log", "nb200_selftest_sincos", "nb200_host_sin", "nb200_host_cos",
+    "nb200_host_sincos", "nb200_selftest_host_sincos",
 ]
 
 _SOLVE_ARGS = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int,
@@ -121,6 +122,14 @@ def load_library(build: bool = False) -> C.CDLL:
     L.nb200_host_threefry2x64_20.argtypes = [C.c_uint64] * 4 + [_u64p]
     L.nb200_host_log.argtypes = [C.c_double]
     L.nb200_host_log.restype = C.c_double
+    L.nb200_selftest_sincos.argtypes = [_dp, _dp, _dp, C.c_int]
+    for name in ("nb200_host_sin", "nb200_host_cos"):
+        getattr(L, name).argtypes = [C.c_double]
+        getattr(L, name).restype = C.c_double
+    L.nb200_host_sincos.argtypes = [_dp, C.c_longlong, _dp, _dp]
+    L.nb200_host_sincos.restype = None
+    L.nb200_selftest_host_sincos.argtypes = [_dp, C.c_longlong, _dp]
+    L.nb200_selftest_host_sincos.restype = C.c_longlong
     _lib = L
     return L
 

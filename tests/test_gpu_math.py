@@ -117,3 +117,32 @@ def test_reciprocal_division_is_ieee_division(gpu_lib):
                                       fast.ctypes.data_as(_dp), ieee.ctypes.data_as(_dp)) == 0
     assert np.array_equal(ieee.view(np.uint64), (a / b).view(np.uint64))  # device == host IEEE
     assert np.array_equal(fast.view(np.uint64), ieee.view(np.uint64))
+
+
+def test_device_sincos_is_libm_sincos(gpu_lib):
+    """Device sin/cos (nb_sincos.cuh) vs the host build of the same source - itself pinned to
+    libm bit for bit on the same arguments - on the inject domain and across every branch."""
+    rng = np.random.default_rng(11)
+    r = (rng.integers(0, 2 ** 64, size=6_000_000, dtype=np.uint64).astype(np.float64)
+         * 2.0 ** -64 + 2.0 ** -65)
+    xs = np.concatenate([
+        2.0 * math.pi * r,                                  # theta of omp3/neutral.c:612
+        (rng.random(1_000_000) - 0.5) * 20.0,
+        np.ldexp(rng.random(1_000_000), -rng.integers(0, 40, 1_000_000)),
+        (rng.random(1_000_000) - 0.5) * 2.0e8,
+        np.array([0.126, 0.855469, 2.426265, math.pi / 2, math.pi, 2.0 * math.pi, 1e-9, 0.0]),
+    ])
+    hi = (xs.view(np.uint64) >> np.uint64(32)) & np.uint64(0x7FFFFFFF)
+    xs = np.ascontiguousarray(xs[hi < 0x419921FB])
+    bad_x = C.c_double(0.0)
+    assert gpu_lib.nb200_selftest_host_sincos(xs.ctypes.data_as(_dp), len(xs),
+                                              C.byref(bad_x)) == 0, bad_x.value
+    hs, hc = np.zeros_like(xs), np.zeros_like(xs)
+    gpu_lib.nb200_host_sincos(xs.ctypes.data_as(_dp), len(xs), hs.ctypes.data_as(_dp),
+                              hc.ctypes.data_as(_dp))
+    ds, dc = np.zeros_like(xs), np.zeros_like(xs)
+    rc = gpu_lib.nb200_selftest_sincos(xs.ctypes.data_as(_dp), ds.ctypes.data_as(_dp),
+                                       dc.ctypes.data_as(_dp), len(xs))
+    assert rc == 0, gpu_lib.nb200_last_error()
+    assert np.array_equal(ds.view(np.uint64), hs.view(np.uint64))
+    assert np.array_equal(dc.view(np.uint64), hc.view(np.uint64))

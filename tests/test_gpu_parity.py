@@ -205,3 +205,28 @@ def test_deferred_step_and_async_fold(gpu_lib, port):
     assert tally_close(sim.tally_to_host(), tally)
     assert all(not bool(t.any()) for t in eng.delta), "delta buffers must end up cleared"
     sim.free()
+
+
+@pytest.mark.parametrize("deck", ["csp_small", "split_small"])
+def test_device_inject_equals_host_inject(gpu_lib, port, ref, deck):
+    """inject_particles on the device (default), on the host with libm (device_inject=0), the
+    oracle port and the unmodified reference all produce the same bank, bit for bit - whole
+    and as shards (global RNG keys)."""
+    prob = build_problem(deck, nparticles=50_000)
+    want = port.inject(prob)
+    assert sum(HostBank.from_aos(ref.inject(prob)).bit_equal(want).values()) == 0
+    for device_inject in (1, 0):
+        gpu_lib.nb200_set_option(b"device_inject", device_inject)
+        try:
+            sim = Simulation(prob, per_particle_counters=False)
+            sim.inject()
+            assert sum(sim.bank_to_host().bit_equal(want).values()) == 0, device_inject
+            sim.free()
+            for r in range(3):
+                part = Simulation(prob, rank=r, nranks=3, per_particle_counters=False)
+                part.inject()
+                got = part.bank_to_host()
+                assert sum(want.slice(part.pid0, part.count).bit_equal(got).values()) == 0
+                part.free()
+        finally:
+            gpu_lib.nb200_set_option(b"device_inject", 1)
