@@ -47,7 +47,8 @@ METRIC = "particle_events_per_sec"
 UNIT = "events/s"
 # algorithmic bytes per event of the event-based model
 B_FACET, B_COLLISION, B_CENSUS, B_DEATH_EXTRA = 200.0, 176.0, 192.0, 16.0
-RED_PEAK_PER_S = 1.9e11  # measured: spread-address red.global.add.f64, L2-resident footprint
+RED_PEAK_PER_S = 1.97e11  # measured best case: red.global.add.f64, spread addresses, L2-resident
+                          # footprint (tools/microbench/red_rate.cu, profiles/r01/red_rate_v2.txt)
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
@@ -452,14 +453,14 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
         # The fused-history lower bound and the measured DRAM traffic say what HBM really sees.
         "fused_bound_bytes_per_launch": fused_history_bytes(timed) / max(hist_launches, 1),
         # The ceiling that does bind facet-dominated decks: every facet, census and death is one
-        # red.global.add.f64 into the tally, and the B200 L2 retires 1.9e11 of those per second
-        # (tools/microbench/red_rate.cu, profiles/r01/red_rate.txt).
+        # red.global.add.f64 into the tally, and the B200 L2 retires 1.97e11 of those per second
+        # (tools/microbench/red_rate.cu, profiles/r01/red_rate_v2.txt).
         "atomic_bound": {
             "achieved": sum(r.facets + r.census + r.deaths for r in timed) / max(kernel_ns, 1) * 1e9,
             "peak": RED_PEAK_PER_S, "unit": "fp64 reductions/s",
             "frac": sum(r.facets + r.census + r.deaths for r in timed) / max(kernel_ns, 1) * 1e9
             / RED_PEAK_PER_S,
-            "peak_source": "measured, profiles/r01/red_rate.txt"},
+            "peak_source": "measured, profiles/r01/red_rate_v2.txt"},
         "note": "k_history is bound by L2 FP64 atomics (facets) and FP64 issue (collisions), "
                 "not by HBM (DESIGN.md 5)",
     }

@@ -2,7 +2,10 @@
 // Each thread issues `iters` red.global.add.f64 to addresses of one of three patterns inside a
 // footprint of `cells` doubles: 0 = uniformly random, 1 = a mesh walk (+-1 or +-nx per step, the
 // tally access pattern of a streaming particle), 2 = random with one FP64 multiply-add chain of
-// `work` operations between reductions (is the rate hidden behind arithmetic?).
+// `work` operations between reductions (is the rate hidden behind arithmetic?), 3 = a cheap
+// strided sweep (cell = (cell + odd stride) & mask: two integer instructions per reduction, so
+// that the loop cannot be the limit), 4 = a straight walk (cell += 1 per step, lanes far
+// apart: the tally pattern of particles streaming along x).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o build/red_rate tools/microbench/red_rate.cu
 #include <cstdio>
 #include <cstdlib>
@@ -23,6 +26,10 @@ __global__ void k_red(double* tally, size_t cells, int nx, int iters, int patter
       if (c < 0) c += cells;
       if ((size_t)c >= cells) c -= cells;
       cell = (size_t)c;
+    } else if (pattern == 3) {
+      cell = (cell + 0x9E3779B1ull) & (cells - 1);  // cells is a power of two
+    } else if (pattern == 4) {
+      cell = (cell + 1) & (cells - 1);
     } else {
       cell = (s >> 20) % cells;
     }
@@ -44,7 +51,7 @@ int main(int argc, char** argv) {
   cudaEventCreate(&e1);
   const int blocks = 148 * 16, threads = 128;
   printf("pattern work footprint_MB reds_per_s\n");
-  for (int pattern = 0; pattern < 3; ++pattern) {
+  for (int pattern = 0; pattern < 5; ++pattern) {
     for (size_t mb : {1, 16, 64, 128, 256, 512}) {
       const size_t cells = mb * (1 << 20) / 8;
       const int work = pattern == 2 ? 40 : 0;

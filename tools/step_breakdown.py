@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 from neutral_b200.decks import build_problem, load_deck  # noqa: E402
 from neutral_b200.host import Simulation, load_library  # noqa: E402
 
-RED_PEAK = 1.9e11
+RED_PEAK = 1.97e11
 
 ap = argparse.ArgumentParser()
 ap.add_argument("deck", nargs="?", default="csp")
