@@ -138,25 +138,15 @@ def reference_rate(deck_name: str, target_seconds: float, steps: int = 1, warmup
         prob = build_problem(deck, nparticles=nparticles)
         d = prob.deck
         tally = np.zeros(d.nx * d.ny)
-        if kind == "reference":
-            bank = eng.inject(prob)
-        else:
-            bank = eng.inject(prob)
+        bank = eng.inject(prob)
+        dead = (lambda: bank["dead"]) if kind == "reference" else (lambda: bank.dead)
         events, seconds = 0, 0.0
         for tt in range(1, d.iterations + 1):
-            if kind == "reference":
-                alive0 = int(np.count_nonzero(bank["dead"] == 0))
-                t0 = time.perf_counter()
-                f, c = eng.step(prob, bank, tt, tally)
-                seconds += time.perf_counter() - t0
-                alive1 = int(np.count_nonzero(bank["dead"] == 0))
-                events += f + c + alive1  # census = processed particles that did not die
-                del alive0
-            else:
-                t0 = time.perf_counter()
-                f, c, p = eng.step(prob, bank, tt, tally)
-                seconds += time.perf_counter() - t0
-                events += f + c + int(np.count_nonzero(bank.dead == 0))
+            t0 = time.perf_counter()
+            counts = eng.step(prob, bank, tt, tally)  # (facets, collisions[, processed])
+            seconds += time.perf_counter() - t0
+            # census events = particles still alive after the step
+            events += counts[0] + counts[1] + int(np.count_nonzero(dead() == 0))
         return events, seconds
 
     # calibrate on a small sample, then size the real one for ~target_seconds per step
