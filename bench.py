@@ -69,7 +69,9 @@ def parse_args():
 # ------------------------------------------------------------------------------ clocks --
 
 class ClockSampler:
-    """Samples nvidia-smi during the timed region (B200_PROFILING.md clocks line)."""
+    """Samples nvidia-smi every 100 ms (B200_PROFILING.md clocks line). It is started before
+    the warm-up so that it is already reporting when the timed regions begin; only samples
+    that arrived inside a timed region (`window(t0, t1)`) count."""
 
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -78,13 +80,14 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []  # (arrival time, csv line)
+        self.windows = []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "200", "-i", str(self.gpu)],
+                 "-lms", "100", "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -92,16 +95,22 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def window(self, t0: float, t1: float):
+        self.windows.append((t0, t1))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        # a sample describes the 100 ms before it arrived
+        inside = [ln for t, ln in self.lines
+                  if any(t0 <= t <= t1 + 0.1 for t0, t1 in self.windows)]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -288,24 +297,25 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        one_step()
-
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        one_step()
+
     launches0 = lib.nb200_kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fence()
+    wall0 = time.time()
     ev0.record()
     timed = []
     for _ in range(args.steps):
         timed += one_step()
     ev1.record()
     fence()
+    sampler.window(wall0, time.time())
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = lib.nb200_kernel_launches() - launches0
-    clocks = sampler.stop() if rank == 0 else None
 
     events = sum(r.events for r in timed)
     kernel_ns = sum(r.kernel_ns for r in timed)
@@ -400,10 +410,13 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
         e2e_res = e2e_run(args.steps)
         fence()
         e2e_s = time.perf_counter() - t0
+        sampler.window(time.time() - e2e_s, time.time())
         last = sets[(args.steps - 1) & 1]
         e2e = {"events": sum(r.events for r in e2e_res), "seconds": e2e_s, "h2d": h2d,
                "d2h": d2h, "tally_sum": float(last.out_tally.sum()),
                "live_out": int((last.out_bank["dead"] == 0).sum())}
+
+    clocks = sampler.stop() if rank == 0 else None  # samples of both timed regions
 
     # ---- reduce over ranks -------------------------------------------------------------
     if world > 1:
