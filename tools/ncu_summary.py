@@ -30,6 +30,8 @@ KEYS = [
     "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
 ]
 
+BYTE_UNITS = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
 
 def main():
     rep = sys.argv[1]
@@ -49,8 +51,11 @@ def main():
                 out.append(f"  {k:86s} {r[i]:>18s} {units[i]}")
         try:
             t = float(vals["gpu__time_duration.sum"])
-            rd, wr = float(vals["dram__bytes_read.sum"]), float(vals["dram__bytes_write.sum"])
-            out.append(f"  -> dram traffic per launch = {rd + wr:.4g} {units[hdr.index('dram__bytes_read.sum')]}"
+            # ncu picks a unit per COLUMN value range (Mbyte for the reads, Gbyte for the writes
+            # of the same launch): convert before adding
+            rd = float(vals["dram__bytes_read.sum"]) * BYTE_UNITS[units[hdr.index("dram__bytes_read.sum")]]
+            wr = float(vals["dram__bytes_write.sum"]) * BYTE_UNITS[units[hdr.index("dram__bytes_write.sum")]]
+            out.append(f"  -> dram traffic per launch = {(rd + wr) / 1e6:.4g} Mbyte"
                        f" over {t:.4g} {units[hdr.index('gpu__time_duration.sum')]}")
             out.append(f"  -> warp execution efficiency = "
                        f"{float(vals['smsp__thread_inst_executed_per_inst_executed.ratio']) / 32 * 100:.1f} %")
