@@ -237,6 +237,10 @@ int nb200_selftest_log(const double* x_host, double* y_host, int n);
 /* fast[i] = a/b through the kernels' reciprocal-based exact division, ieee[i] = a/b. */
 int nb200_selftest_div(const double* a_host, const double* b_host, int n, double* fast_host,
                        double* ieee_host);
+/* The kernels' straight-line division / reciprocal / square-root cores (csrc/nb_fastmath.cuh)
+ * next to the plain operators: out_host holds 6 arrays of n doubles - core a/b, a/b, core 1/b,
+ * 1/b, core sqrt|a|, sqrt|a|. */
+int nb200_selftest_fastmath(const double* a_host, const double* b_host, int n, double* out_host);
 int nb200_selftest_cs(const double* keys_host, const double* values_host, int nentries,
                       const double* energies_host, int n, int* index_host,
                       double* value_host);

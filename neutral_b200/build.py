@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, os.environ.get("NB200_LIB", "libneutral_b200.so"))
 SOURCES = ["transport.cu", "stage.cu", "pipeline.cu", "history.cu", "capi.cu"]
 HEADERS = ["transport.cuh", "nb_device.cuh", "nb_bank.cuh", "nb_math.cuh", "nb_history.cuh",
-           "nb_sincos.cuh", "glibc_log_table.inc", "glibc_sincos_table.inc",
+           "nb_sincos.cuh", "nb_fastmath.cuh", "glibc_log_table.inc", "glibc_sincos_table.inc",
            os.path.join("..", "..", "include", "neutral_b200.h")]
 
 NVCC_FLAGS = [

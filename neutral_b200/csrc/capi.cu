@@ -86,6 +86,13 @@ struct Context {
   unsigned long long* d_totals = nullptr;
   unsigned long long* h_totals = nullptr;  // pinned
   cudaEvent_t ev_begin = nullptr, ev_mid = nullptr, ev_end = nullptr;  // phase timing
+  // The density tile maps are only read by the event loop: they are staged on a side stream
+  // beside the begin-step / sort kernels (fork after the previous history kernel, join
+  // before the next one).
+  cudaStream_t stage_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_tiles = nullptr;
+  int opt_stage_overlap = 1;
+  int opt_history_smem_pad = 0;  // occupancy probe: extra dynamic shared memory per CTA
   unsigned* d_bins = nullptr;  // histogram + cursors of the per-step sort
   unsigned* d_n_live = nullptr;
   int bins_capacity = 0;
@@ -185,6 +192,9 @@ int ensure_ready() {
   CU_TRY(cudaEventCreate(&g.ev_begin));
   CU_TRY(cudaEventCreate(&g.ev_mid));
   CU_TRY(cudaEventCreate(&g.ev_end));
+  CU_TRY(cudaStreamCreateWithFlags(&g.stage_stream, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&g.ev_tiles, cudaEventDisableTiming));
   CU_TRY(cudaMalloc(&g.d_n_live, sizeof(unsigned)));
   g.ready = true;
   return 0;
@@ -344,7 +354,7 @@ void stage_tables(StepArgs& a) {
   a.cs_a = CsStage{d_kv_a, d_bk_a, g.cs_a_par.bits0, g.cs_a_par.shift, g.cs_a_par.nb, a.a_n};
 }
 
-void stage_tiles(StepArgs& a) {
+void stage_tiles(StepArgs& a, cudaStream_t st) {
   const int nfine = (((a.nx - 1) >> kTileShift) + 1) * (((a.ny - 1) >> kTileShift) + 1);
   const int ncoarse = (((a.nx - 1) >> kCoarseShift) + 1) * (((a.ny - 1) >> kCoarseShift) + 1);
   if (g.tile_capacity < nfine + ncoarse) {
@@ -353,7 +363,7 @@ void stage_tiles(StepArgs& a) {
     g.tile_capacity = nfine + ncoarse;
   }
   g.launches += launch_stage_tiles(a.density, a.nx, a.ny, g.d_tile_rho, g.d_tile_rho + nfine,
-                                   &a.tiles, g.stream);
+                                   &a.tiles, st);
 }
 
 void finish_step(uint64_t* facet_events, uint64_t* collision_events);
@@ -414,8 +424,15 @@ void run_step(Bank* bank, int nx, int ny, uint64_t master_key, double dt, int nt
       g.l2_limit_set = true;
     }
     // P0: restage the read-only inputs (cross-section tables, density tile map)
+    const bool overlap = g.opt_stage_overlap != 0;
+    if (overlap) {
+      CU_FATAL(cudaEventRecord(g.ev_fork, g.stream));
+      CU_FATAL(cudaStreamWaitEvent(g.stage_stream, g.ev_fork, 0));
+      stage_tiles(a, g.stage_stream);
+      CU_FATAL(cudaEventRecord(g.ev_tiles, g.stage_stream));
+    }
     stage_tables(a);
-    stage_tiles(a);
+    if (!overlap) stage_tiles(a, g.stream);
     // P1-P3: begin-step set-up, classification and counting sort into the double buffer
     SortArgs s{};
     s.tile_shift = g.opt_tile_shift;
@@ -447,12 +464,13 @@ void run_step(Bank* bank, int nx, int ny, uint64_t master_key, double dt, int nt
     g.launches += launch_sort_phase(a, s, bank->alt, g.stream);
     std::swap(bank->cur, bank->alt);
     a.bank = bank->cur;
+    if (overlap) CU_FATAL(cudaStreamWaitEvent(g.stream, g.ev_tiles, 0));
     CU_FATAL(cudaEventRecord(g.ev_mid, g.stream));
     // P4: event loop over the sorted live prefix
     g.launches += launch_history(a, g.d_n_live, s.n_upper, g.opt_fast_div != 0,
                                  g.opt_tally_prereduce != 0,
                                  g.opt_l2_persist ? g.d_cs_stage : nullptr, g.cs_stage_bytes,
-                                 g.stream);
+                                 g.opt_history_smem_pad, g.stream);
   } else {
     CU_FATAL(cudaEventRecord(g.ev_mid, g.stream));
     g.launches += launch_history_direct(a, g.stream);
@@ -1082,6 +1100,8 @@ extern "C" int nb200_set_option(const char* name, int value) {
   else if (strcmp(name, "l2_persist") == 0) slot = &g.opt_l2_persist;
   else if (strcmp(name, "defer_finish") == 0) slot = &g.opt_defer_finish;
   else if (strcmp(name, "device_inject") == 0) slot = &g.opt_device_inject;
+  else if (strcmp(name, "stage_overlap") == 0) slot = &g.opt_stage_overlap;
+  else if (strcmp(name, "history_smem_pad") == 0) slot = &g.opt_history_smem_pad;
   if (!slot) {
     set_error("nb200_set_option: unknown option '%s'", name);
     return -3;
@@ -1190,6 +1210,25 @@ extern "C" int nb200_selftest_div(const double* a_host, const double* b_host, in
   CU_TRY(cudaMemcpyAsync(ieee_host, d[3], sizeof(double) * n, cudaMemcpyDeviceToHost, g.stream));
   CU_TRY(cudaStreamSynchronize(g.stream));
   for (auto& p : d) cudaFree(p);
+  return 0;
+}
+
+extern "C" int nb200_selftest_fastmath(const double* a_host, const double* b_host, int n,
+                                       double* out_host) {
+  if (ensure_ready() != 0) return -1;
+  double *d_a = nullptr, *d_b = nullptr, *d_o = nullptr;
+  CU_TRY(cudaMalloc(&d_a, sizeof(double) * n));
+  CU_TRY(cudaMalloc(&d_b, sizeof(double) * n));
+  CU_TRY(cudaMalloc(&d_o, sizeof(double) * 6 * (size_t)n));
+  CU_TRY(cudaMemcpyAsync(d_a, a_host, sizeof(double) * n, cudaMemcpyHostToDevice, g.stream));
+  CU_TRY(cudaMemcpyAsync(d_b, b_host, sizeof(double) * n, cudaMemcpyHostToDevice, g.stream));
+  g.launches += launch_selftest_fastmath(d_a, d_b, d_o, n, g.stream);
+  CU_TRY(cudaMemcpyAsync(out_host, d_o, sizeof(double) * 6 * (size_t)n, cudaMemcpyDeviceToHost,
+                         g.stream));
+  CU_TRY(cudaStreamSynchronize(g.stream));
+  cudaFree(d_a);
+  cudaFree(d_b);
+  cudaFree(d_o);
   return 0;
 }
 

@@ -20,7 +20,6 @@
 //    axis reloads its next edge - issued before the event's arithmetic, consumed after it;
 //  * the density of the entered cell comes from the per-step tile maps (stage.cu) unless the
 //    tile is mixed; cross sections come from the staged tables through the bucket index;
-//  * the tally index cy*nx+cx is carried along instead of being rebuilt.
 //
 // Compiled with -fmad=false: the only fused operations are the explicit fma() of nb_log and
 // div_by_known.
@@ -28,9 +27,6 @@
 
 namespace nb {
 
-#ifndef NB_EARLY_DRAW
-#define NB_EARLY_DRAW 1
-#endif
 #ifndef NB_HISTORY_MIN_BLOCKS
 #define NB_HISTORY_MIN_BLOCKS 6
 #endif
@@ -51,6 +47,7 @@ struct Parked {
   double rho[kHistoryThreads];
   double edep[kHistoryThreads];
   int origin[kHistoryThreads];  // index in injection order: RNG key and counter slot
+  unsigned nc[kHistoryThreads];  // collisions so far this step = the RNG counter state
 };
 
 template <bool kFastDiv, bool kPreReduce>
@@ -62,10 +59,12 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
 #else
   double park_e, park_Sig_s, park_p_absorb, park_rho, park_edep;
   int park_origin;
+  unsigned park_nc;
 #define PARKED(name) park_##name
 #endif
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned nf = 0, nc = 0, census = 0, processed = 0, died = 0;
+  unsigned nf = 0, census = 0, processed = 0, died = 0;
+  PARKED(nc) = 0;
 
   int4 m = make_int4(0, 0, 1, 0);
   if (slot < (int)*n_live) m = a.bank.meta[slot];
@@ -79,7 +78,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
     double x = pos.x, y = pos.y, ox = dir.x, oy = dir.y, w = ew.y;
     double dtc = tm.x, mfp = tm.y;
     int cx = m.x, cy = m.y;
-    int cell = cy * a.nx + cx;  // tally / density index, carried along
+#define NB_CELL (cy * a.nx + cx)  // tally / density index of the current cell
     unsigned flags = 0;
     PARKED(e) = ew.x;
     PARKED(edep) = 0.0;
@@ -97,7 +96,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
         rho = fine_value(a, cx, cy);
         if (is_mixed_tile(rho)) {
           flags |= kFlagFineMixed;
-          rho = __ldg(a.density + cell);
+          rho = __ldg(a.density + NB_CELL);
         }
       }
       PARKED(rho) = rho;
@@ -137,11 +136,17 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
         nf++;
         double q_mfp, q_dtc;
         if (kFastDiv && (flags & kFlagInvStale)) {  // first facet after a collision / new density
-          v_inv = 1.0 / v;
-          d.cell_mfp_inv = 1.0 / d.cell_mfp;
           flags &= ~(kFlagInvStale | kFlagDivOk);
-          if (safe_exponent(v)) flags |= kFlagSpeedOk;
-          if (safe_exponent(d.cell_mfp)) flags |= kFlagCellMfpOk;
+          if (fm_safe(v) & fm_safe(d.cell_mfp)) {  // both reciprocals side by side
+            v_inv = rcp_core(v);
+            d.cell_mfp_inv = rcp_core(d.cell_mfp);
+            flags |= kFlagDivOk;
+          } else {
+            v_inv = 1.0 / v;
+            d.cell_mfp_inv = 1.0 / d.cell_mfp;
+            if (safe_exponent(v)) flags |= kFlagSpeedOk;
+            if (safe_exponent(d.cell_mfp)) flags |= kFlagCellMfpOk;
+          }
         }
         if (kFastDiv && (flags & kFlagDivOk) == kFlagDivOk && safe_exponent(d_facet)) {
           q_mfp = div_by_known_unchecked(d_facet, d.cell_mfp, d.cell_mfp_inv);
@@ -159,7 +164,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
           PARKED(edep) = 0.0;
           flags &= ~kFlagPending;
         }
-        tally_add<kPreReduce>(a.tally, cell, edep * a.inv_ntotal);
+        tally_add<kPreReduce>(a.tally, NB_CELL, edep * a.inv_ntotal);
         x += d_facet * ox;
         y += d_facet * oy;
         // the edge load is consumed here, after the arithmetic it overlapped with
@@ -169,7 +174,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
         if (reflect) {
           if (x_facet) { ox = -ox; uxi = -uxi; } else { oy = -oy; uyi = -uyi; }
         } else {
-          if (x_facet) { cx = cn; cell += s; } else { cy = cn; cell += s * a.nx; }
+          if (x_facet) cx = cn; else cy = cn;
           // :372-378 - the macroscopic cross sections follow the density of the new cell.
           // Inside a uniform coarse tile the density cannot change; otherwise the coarse map,
           // the fine map and finally the mesh itself are consulted.
@@ -203,7 +208,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
                 continue;  // still inside the same uniform fine tile
               }
             }
-            if (!known) rho_new = __ldg(a.density + cell);  // mixed fine tile: the mesh itself
+            if (!known) rho_new = __ldg(a.density + NB_CELL);  // mixed fine tile: the mesh itself
             if (double_to_bits(rho_new) != double_to_bits(PARKED(rho))) {
               PARKED(rho) = rho_new;
               nd = number_density(rho_new);
@@ -219,7 +224,8 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
       } else if (collide) {
 #endif
         // ---- collision_event, :209-300
-        nc++;
+        const unsigned nc = PARKED(nc) + 1;
+        PARKED(nc) = nc;
         const uint64_t pkey = a.pid0 + (uint64_t)(unsigned)PARKED(origin);
         const double e = PARKED(e);
         const double p_absorb = PARKED(p_absorb);
@@ -228,54 +234,73 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
         y += d_coll * oy;
         double a0, a1;
         random_pair(pkey, a.master_key, 2ull * nc - 1ull, a0, a1);
-#if NB_EARLY_DRAW
         // The draw of :294 does not depend on the outcome of the collision: taken here, its
         // Threefry evaluation interleaves with the one above (two independent chains).
         const double neglog = -nb_log(random_first(pkey, a.master_key, 2ull * nc), a.logt);
-#endif
-        // :296 - the time to census shrinks by the flight time at the pre-collision speed
-        double q_dtc;
-        if (kFastDiv && (flags & kFlagSpeedOk) && safe_exponent(d_coll))
-          q_dtc = div_by_known_unchecked(d_coll, v, v_inv);
-        else
-          q_dtc = d_coll / v;
+        // :296 - the time to census shrinks by the flight time at the pre-collision speed.
+        // Branch-free core beside the Threefry chains; the plain operator takes over below
+        // for operands outside the core's range.
+        const bool q_ok = kFastDiv && (fm_safe(d_coll) & fm_safe(v));
+        double q_dtc = kFastDiv ? div_core(d_coll, v) : d_coll / v;
+        if (kFastDiv && !q_ok) q_dtc = d_coll / v;
         if (a0 < p_absorb) {
           w *= (1.0 - p_absorb);
           if (e < kMinEnergyOfInterest) {  // :243-252 - the history ends here
             flags |= kFlagDead;
-            tally_add<kPreReduce>(a.tally, cell, edep * a.inv_ntotal);
+            tally_add<kPreReduce>(a.tally, NB_CELL, edep * a.inv_ntotal);
             break;
           }
           // Energy and direction are unchanged: the lookups of :285-291 return the values
           // already held, so nothing that depends on them needs recomputing.
+          mfp = neglog / PARKED(Sig_s);
         } else {
-          const double mu = 1.0 - 2.0 * a1;
-          const double e_num = e * ((kMassNo * kMassNo + (2.0 * kMassNo) * mu) + 1.0);
-          const double e_new = kFastDiv ? NB_DIV_CONST(e_num, (kMassNo + 1.0) * (kMassNo + 1.0))
-                                        : e_num / ((kMassNo + 1.0) * (kMassNo + 1.0));
-          const double ct = 0.5 * ((kMassNo + 1.0) * sqrt(e_new / e) -
-                                   (kMassNo - 1.0) * sqrt(e / e_new));
-          const double st = sqrt(1.0 - ct * ct);
-          const double nox = ox * ct - oy * st;
-          const double noy = ox * st + oy * ct;
-          ox = nox;
-          oy = noy;
-          PARKED(e) = e_new;
-          derive(a, e_new, nd, d, PARKED(Sig_s), PARKED(p_absorb), flags);
-          v = kFastDiv ? speed_of_fast(e_new) : speed_of(e_new);
-          flags = (flags & ~kFlagSpeedOk) | kFlagInvStale;  // v_inv is recomputed on demand
-          uxi = 1.0 / (ox * v);
-          uyi = 1.0 / (oy * v);
-          ex = target_edge(a.edgex, cx, axis_step(ox));
-          ey = target_edge(a.edgey, cy, axis_step(oy));
+          bool done = false;
+          if (kFastDiv && a.same_keys) {
+            // The whole scatter as one basic block (nb_history.cuh). It writes the state in
+            // place; what the plain code below would need again if an operand turns out to be
+            // outside the block's range is parked in the two slots this branch no longer
+            // reads (the direction) or recomputed (the second random number).
+            PARKED(Sig_s) = ox;
+            PARKED(p_absorb) = oy;
+            double e_new, S_s, pa;
+            done = scatter_fast_same_grid(a, e, a1, nd, neglog, cx, cy, ox, oy, v, uxi, uyi, ex,
+                                          ey, mfp, d, e_new, S_s, pa);
+            if (done) {
+              PARKED(e) = e_new;
+              PARKED(Sig_s) = S_s;
+              PARKED(p_absorb) = pa;
+              flags = (flags & ~(kFlagSpeedOk | kFlagCellMfpOk)) | kFlagInvStale;
+            } else {
+              ox = PARKED(Sig_s);
+              oy = PARKED(p_absorb);
+              random_pair(pkey, a.master_key, 2ull * nc - 1ull, a0, a1);
+            }
+          }
+          if (!done) {
+            const double mu = 1.0 - 2.0 * a1;
+            const double e_num = e * ((kMassNo * kMassNo + (2.0 * kMassNo) * mu) + 1.0);
+            const double e_new = kFastDiv ? NB_DIV_CONST(e_num, (kMassNo + 1.0) * (kMassNo + 1.0))
+                                          : e_num / ((kMassNo + 1.0) * (kMassNo + 1.0));
+            const double ct = 0.5 * ((kMassNo + 1.0) * sqrt(e_new / e) -
+                                     (kMassNo - 1.0) * sqrt(e / e_new));
+            const double st = sqrt(1.0 - ct * ct);
+            const double nox = ox * ct - oy * st;
+            const double noy = ox * st + oy * ct;
+            ox = nox;
+            oy = noy;
+            PARKED(e) = e_new;
+            derive(a, e_new, nd, d, PARKED(Sig_s), PARKED(p_absorb), flags);
+            v = kFastDiv ? speed_of_fast(e_new) : speed_of(e_new);
+            flags = (flags & ~kFlagSpeedOk) | kFlagInvStale;  // v_inv is recomputed on demand
+            uxi = 1.0 / (ox * v);
+            uyi = 1.0 / (oy * v);
+            ex = target_edge(a.edgex, cx, axis_step(ox));
+            ey = target_edge(a.edgey, cy, axis_step(oy));
+            mfp = neglog / PARKED(Sig_s);
+          }
         }
         PARKED(edep) = edep;
         flags |= kFlagPending;
-#if NB_EARLY_DRAW
-        mfp = neglog / PARKED(Sig_s);
-#else
-        mfp = -nb_log(random_first(pkey, a.master_key, 2ull * nc), a.logt) / PARKED(Sig_s);
-#endif
         dtc -= q_dtc;
       } else {
         // ---- census_event, :383-405
@@ -285,7 +310,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
         mfp -= d_census / d.cell_mfp;
         double edep = deposition(w, d_census, d.stb, d.heat, nd);
         if (flags & kFlagPending) edep = PARKED(edep) + edep;
-        tally_add<kPreReduce>(a.tally, cell, edep * a.inv_ntotal);
+        tally_add<kPreReduce>(a.tally, NB_CELL, edep * a.inv_ntotal);
         dtc = 0.0;
         break;
       }
@@ -299,11 +324,12 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
     const int origin = PARKED(origin);
     a.bank.meta[slot] = make_int4(cx, cy, (int)died, origin);
     if (a.p_facets) a.p_facets[origin] += nf;
-    if (a.p_collisions) a.p_collisions[origin] += nc;
+    if (a.p_collisions) a.p_collisions[origin] += PARKED(nc);
     if (a.p_census) a.p_census[origin] += census;
   }
-  flush_totals(a.totals, nf, nc, processed, census, died);
+  flush_totals(a.totals, nf, PARKED(nc), processed, census, died);
 #undef PARKED
+#undef NB_CELL
 }
 
 static inline int blocks_for(int n, int threads) { return (n + threads - 1) / threads; }
@@ -312,12 +338,25 @@ static inline int blocks_for(int n, int threads) { return (n + threads - 1) / th
 // access-policy window that keeps it persisting in L2 (north_star phase 3), while the rest of
 // the kernel's traffic - the tally atomics above all - streams through the remainder.
 int launch_history(const StepArgs& a, const unsigned* n_live, int n_upper, bool fast_div,
-                   bool prereduce, const void* pin, size_t pin_bytes, cudaStream_t st) {
+                   bool prereduce, const void* pin, size_t pin_bytes, int smem_pad,
+                   cudaStream_t st) {
   if (n_upper <= 0) return 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(blocks_for(n_upper, kHistoryThreads));
   cfg.blockDim = dim3(kHistoryThreads);
   cfg.stream = st;
+  if (smem_pad > 0) {
+    // Occupancy probe (option history_smem_pad): unused dynamic shared memory that lowers
+    // the number of resident CTAs per SM without touching the code.
+    static int granted = 0;
+    if (smem_pad > granted) {
+      cudaFuncSetAttribute(k_history<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pad);
+      cudaFuncSetAttribute(k_history<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pad);
+      cudaFuncSetAttribute(k_history<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pad);
+      granted = smem_pad;
+    }
+    cfg.dynamicSmemBytes = (size_t)smem_pad;
+  }
   cudaLaunchAttribute attr[1];
   if (pin && pin_bytes) {
     attr[0].id = cudaLaunchAttributeAccessPolicyWindow;

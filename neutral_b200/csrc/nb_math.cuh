@@ -143,31 +143,43 @@ NB_HD uint64_t double_to_bits(double d) {
 #endif
 }
 
+// The same numbers as compile-time constants: the polynomial coefficients then reach the
+// FP64 pipe as constant-bank operands instead of through eighteen loads per call; only the
+// {invc, logc} pair, whose index differs from lane to lane, is read from the table in memory.
+constexpr double kLogData[2 + 5 + 11 + 256] = {
+#include "glibc_log_table.inc"
+};
+#define NB_LOG_C(name, index) constexpr double name = kLogData[index]
+
 NB_HD double nb_log(double x, const LogTable* __restrict__ L) {
+  NB_LOG_C(ln2hi, 0); NB_LOG_C(ln2lo, 1);
+  NB_LOG_C(A0, 2); NB_LOG_C(A1, 3); NB_LOG_C(A2, 4); NB_LOG_C(A3, 5); NB_LOG_C(A4, 6);
+  NB_LOG_C(B0, 7); NB_LOG_C(B1, 8); NB_LOG_C(B2, 9); NB_LOG_C(B3, 10); NB_LOG_C(B4, 11);
+  NB_LOG_C(B5, 12); NB_LOG_C(B6, 13); NB_LOG_C(B7, 14); NB_LOG_C(B8, 15); NB_LOG_C(B9, 16);
+  NB_LOG_C(B10, 17);
   const uint64_t ix = double_to_bits(x);
   if (ix - 0x3fee000000000000ull < 0x0003090000000000ull) {
     // 0.9375 <= x < 1.0647: polynomial in r = x - 1 with a split high/low square term.
     if (ix == 0x3ff0000000000000ull) return 0.0;
-    const double* B = L->b;
     const double r = x - 1.0;
     const double r2 = r * r;
     const double r3 = r * r2;
-    double p1 = fma(r, B[2], B[1]);
-    double p2 = fma(r, B[5], B[4]);
-    double p3 = fma(r, B[8], B[7]);
-    p1 = fma(r2, B[3], p1);
-    p2 = fma(r2, B[6], p2);
-    p3 = fma(r2, B[9], p3);
-    p3 = fma(r3, B[10], p3);
+    double p1 = fma(r, B2, B1);
+    double p2 = fma(r, B5, B4);
+    double p3 = fma(r, B8, B7);
+    p1 = fma(r2, B3, p1);
+    p2 = fma(r2, B6, p2);
+    p3 = fma(r2, B9, p3);
+    p3 = fma(r3, B10, p3);
     double q = fma(p3, r3, p2);
     q = fma(q, r3, p1);
     const double t = fma(r, 0x1p27, r);
     const double rhi = fma(-0x1p27, r, t);
     const double rlo = r - rhi;
     const double h2 = rhi * rhi;
-    const double hi = fma(h2, B[0], r);
-    const double lo = fma(h2, B[0], r - hi);
-    double u = B[0] * rlo;
+    const double hi = fma(h2, B0, r);
+    const double lo = fma(h2, B0, r - hi);
+    double u = B0 * rlo;
     u = fma(u, r + rhi, lo);
     q = fma(q, r3, u);
     return hi + q;
@@ -176,20 +188,24 @@ NB_HD double nb_log(double x, const LogTable* __restrict__ L) {
   const int i = (int)((tmp >> 45) & 127);
   const int k = (int)((int64_t)tmp >> 52);
   const double z = bits_to_double(ix - (tmp & 0xfff0000000000000ull));
+#if defined(__CUDA_ARCH__)
+  const double2 tc = __ldg(reinterpret_cast<const double2*>(L->t) + i);  // one 16-byte load
+  const double invc = tc.x, logc = tc.y;
+#else
   const double invc = L->t[2 * i];
   const double logc = L->t[2 * i + 1];
+#endif
   const double kd = (double)k;
-  const double* A = L->a;
-  const double w = fma(kd, L->ln2hi, logc);
+  const double w = fma(kd, ln2hi, logc);
   const double r = fma(z, invc, -1.0);
-  const double pa = fma(r, A[2], A[1]);
+  const double pa = fma(r, A2, A1);
   const double hi = r + w;
   const double r2 = r * r;
   double lo = (w - hi) + r;
-  lo = fma(kd, L->ln2lo, lo);
+  lo = fma(kd, ln2lo, lo);
   const double r3 = r * r2;
-  double pb = fma(r, A[4], A[3]);
-  lo = fma(r2, A[0], lo);
+  double pb = fma(r, A4, A3);
+  lo = fma(r2, A0, lo);
   pb = fma(pb, r2, pa);
   return fma(r3, pb, lo) + hi;
 }
@@ -210,13 +226,17 @@ NB_HD double speed_of(double e) { return sqrt(((2.0 * e) * kEvToJ) / kParticleMa
 // Path-length heating estimator                                 omp3/neutral.c:474-495
 // heat_response depends on (E, sigma_a/sigma_t) only, so callers may cache it between
 // collisions; the value is the same either way.
-NB_HD double heating_response(double e, double sig_a, double sig_t) {
+// `q` is the quotient sigma_a / sigma_t of :482,486 (the same division twice).
+NB_HD double heating_response_q(double e, double q) {
   constexpr double c1 =
       (kMassNo * kMassNo + kMassNo + 1) / ((kMassNo + 1) * (kMassNo + 1));
-  const double q = sig_a / sig_t;
   const double absorb_heat = q * 0.0;
   const double scatter_heat = (1.0 - q) * (e * c1);
   return (e - scatter_heat) - absorb_heat;
+}
+
+NB_HD double heating_response(double e, double sig_a, double sig_t) {
+  return heating_response_q(e, sig_a / sig_t);
 }
 
 NB_HD double deposition(double weight, double path, double sig_t_barns, double response,

@@ -20,6 +20,7 @@
 // the reference's own expression whenever one of its inputs changes, so the values are the
 // ones the reference would recompute each iteration.
 #include "nb_device.cuh"
+#include "nb_fastmath.cuh"
 #include "transport.cuh"
 
 namespace nb {
@@ -229,6 +230,20 @@ __global__ void k_selftest_div(const double* a, const double* b, double* fast, d
   ieee[i] = a[i] / b[i];
 }
 
+// Self-test hook: the straight-line cores of nb_fastmath.cuh next to the plain operators.
+// out = 6 arrays of n: div_core(a,b), a/b, rcp_core(b), 1/b, sqrt_core(|a|), sqrt(|a|).
+__global__ void k_selftest_fastmath(const double* a, const double* b, double* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = a[i], y = b[i], ax = fabs(x);
+  out[i] = div_core(x, y);
+  out[(size_t)n + i] = x / y;
+  out[2 * (size_t)n + i] = rcp_core(y);
+  out[3 * (size_t)n + i] = 1.0 / y;
+  out[4 * (size_t)n + i] = sqrt_core(ax);
+  out[5 * (size_t)n + i] = sqrt(ax);
+}
+
 // ------------------------------------------------------------------------------------
 // Launch wrappers
 // ------------------------------------------------------------------------------------
@@ -245,6 +260,12 @@ int launch_sort_phase(const StepArgs& a, const SortArgs& s, const BankView& alt,
   k_scan_bins<<<nchunks, kScanThreads, 0, st>>>(s, s.chunk_sum);
   k_scatter<<<blocks_for(s.n, 256), 256, 0, st>>>(a.bank, alt, s);
   return 5;
+}
+
+int launch_selftest_fastmath(const double* a, const double* b, double* out, int n,
+                             cudaStream_t st) {
+  k_selftest_fastmath<<<blocks_for(n, 256), 256, 0, st>>>(a, b, out, n);
+  return 1;
 }
 
 int launch_selftest_div(const double* a, const double* b, double* fast, double* ieee, int n,

@@ -15,7 +15,8 @@ int launch_history_direct(const StepArgs& a, cudaStream_t st);
 int launch_sort_phase(const StepArgs& a, const SortArgs& s, const BankView& alt,
                       cudaStream_t st);
 int launch_history(const StepArgs& a, const unsigned* n_live, int n_upper, bool fast_div,
-                   bool prereduce, const void* pin, size_t pin_bytes, cudaStream_t st);
+                   bool prereduce, const void* pin, size_t pin_bytes, int smem_pad,
+                   cudaStream_t st);
 // Per-step staging of the read-only inputs (stage.cu).
 int launch_stage_cs(const double* keys, const double* vals, int n, double2* kv, int* bucket,
                     unsigned long long bits0, int shift, int nb, const double* twin_keys,
@@ -25,6 +26,8 @@ int launch_stage_tiles(const double* density, int nx, int ny, double* fine, doub
                        TileMap* map, cudaStream_t st);
 int launch_selftest_div(const double* a, const double* b, double* fast, double* ieee, int n,
                         cudaStream_t st);
+int launch_selftest_fastmath(const double* a, const double* b, double* out, int n,
+                             cudaStream_t st);
 
 // inject_particles on the device (transport.cu: k_inject). Edges are device pointers.
 struct SinCosTable;

@@ -48,7 +48,7 @@ EXPORTED_SYMBOLS = [
     "nb200_memcpy_d2h", "nb200_memcpy_h2d_async", "nb200_memcpy_d2h_async", "nb200_bank_view",
     "nb200_bank_import", "nb200_memset_d", "nb200_synchronize", "nb200_set_option",
     "nb200_solve_finish", "nb200_last_step_stats", "nb200_kernel_launches", "nb200_selftest_rng_log",
-    "nb200_selftest_log", "nb200_selftest_div", "nb200_selftest_cs", "nb200_host_threefry2x64_20",
+    "nb200_selftest_log", "nb200_selftest_div", "nb200_selftest_fastmath", "nb200_selftest_cs", "nb200_host_threefry2x64_20",
     "nb200_host_log", "nb200_selftest_sincos", "nb200_host_sin", "nb200_host_cos",
     "nb200_host_sincos", "nb200_selftest_host_sincos",
 ]
@@ -118,6 +118,7 @@ def load_library(build: bool = False) -> C.CDLL:
                                          _dp, _dp]
     L.nb200_selftest_log.argtypes = [_dp, _dp, C.c_int]
     L.nb200_selftest_div.argtypes = [_dp, _dp, C.c_int, _dp, _dp]
+    L.nb200_selftest_fastmath.argtypes = [_dp, _dp, C.c_int, _dp]
     L.nb200_selftest_cs.argtypes = [_dp, _dp, C.c_int, _dp, C.c_int, _ip, _dp]
     L.nb200_host_threefry2x64_20.argtypes = [C.c_uint64] * 4 + [_u64p]
     L.nb200_host_log.argtypes = [C.c_double]

@@ -119,6 +119,44 @@ def test_reciprocal_division_is_ieee_division(gpu_lib):
     assert np.array_equal(fast.view(np.uint64), ieee.view(np.uint64))
 
 
+def test_straight_line_cores_are_the_ieee_operators(gpu_lib):
+    """div_core / rcp_core / sqrt_core (nb_fastmath.cuh: the compiler's own fast-path sequences
+    without its range branch) against `/`, `1.0/` and sqrt() on the device and against numpy on
+    the host, bit for bit, over the operand range the kernels admit them for
+    (2^-255 <= |v| < 2^257) - mid-range magnitudes, the scatter kinematics' ratios near 1,
+    mantissas at both ends of a binade, and the extremes of the admitted range."""
+    rng = np.random.default_rng(2024)
+    n = 6_000_000
+    def operands(seed_shift):
+        r = np.random.default_rng(2024 + seed_shift)
+        return np.ascontiguousarray(np.concatenate([
+            10.0 ** r.uniform(-30, 30, n // 3) * r.choice([-1.0, 1.0], n // 3),
+            1.0 + (r.random(n // 6) - 0.5) * 0.08,                     # e'/e of a scatter
+            2.0 ** r.uniform(-254.9, 256.9, n // 6),                   # the whole admitted range
+            (1.0 + r.integers(0, 2 ** 22, n // 6) * 2.0 ** -52) * 2.0 ** r.integers(-40, 40, n // 6),
+            (2.0 - r.integers(1, 2 ** 22, n // 6) * 2.0 ** -52) * 2.0 ** r.integers(-40, 40, n // 6),
+        ]))
+    a, b = operands(0), operands(1)
+    out = np.zeros(6 * len(a))
+    assert gpu_lib.nb200_selftest_fastmath(a.ctypes.data_as(_dp), b.ctypes.data_as(_dp), len(a),
+                                           out.ctypes.data_as(_dp)) == 0
+    core_div, div, core_rcp, rcp, core_sqrt, sqrt_ = out.reshape(6, -1).view(np.uint64)
+    assert np.array_equal(div, (a / b).view(np.uint64))
+    assert np.array_equal(rcp, (1.0 / b).view(np.uint64))
+    assert np.array_equal(sqrt_, np.sqrt(np.abs(a)).view(np.uint64))
+    # quotients of admitted operands can leave the normal range only beyond 2^+-512: all finite
+    assert np.array_equal(core_div, div)
+    assert np.array_equal(core_rcp, rcp)
+    assert np.array_equal(core_sqrt, sqrt_)
+    # a numerator of exactly +0 (an energy on a grid point of the cross-section table)
+    z = np.zeros(1024)
+    bz = np.ascontiguousarray(10.0 ** rng.uniform(-20, 20, 1024))
+    outz = np.zeros(6 * 1024)
+    assert gpu_lib.nb200_selftest_fastmath(z.ctypes.data_as(_dp), bz.ctypes.data_as(_dp), 1024,
+                                           outz.ctypes.data_as(_dp)) == 0
+    assert not outz[:1024].view(np.uint64).any()
+
+
 def test_device_sincos_is_libm_sincos(gpu_lib):
     """Device sin/cos (nb_sincos.cuh) vs the host build of the same source - itself pinned to
     libm bit for bit on the same arguments - on the inject domain and across every branch."""
