@@ -373,15 +373,31 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
                                                   nbytes(h_bank[k]), up.cuda_stream), "h2d bank")
             ws.uploaded.record(up)
 
+        trace = {} if os.environ.get("NB200_E2E_TRACE") else None
+
+        def lap(name, t0):
+            if trace is not None:
+                trace[name] = trace.get(name, 0.0) + time.perf_counter() - t0
+            return time.perf_counter()
+
         def transport(ws):
+            t = time.perf_counter()
             torch.cuda.current_stream().wait_event(ws.uploaded)
+            if trace is not None:
+                ws.uploaded.synchronize()
+                t = lap("wait_upload", t)
             _check(lib.nb200_bank_import(ws.sim.bank), "bank_import")
             ws.sim.tally.zero()
+            t = lap("import+zero (enqueue)", t)
             if world > 1:
                 out = run_timesteps(ws.engine, d.iterations, world, dist)
             else:
-                out = [ws.sim.step(tt) for tt in range(1, d.iterations + 1)]
+                out = []
+                for tt in range(1, d.iterations + 1):
+                    out.append(ws.sim.step(tt))
+                    t = lap("step %d" % tt if tt <= 2 else "steps 3..", t)
             _check(lib.nb200_bank_export(ws.sim.bank), "bank_export")  # synchronises
+            lap("export", t)
             return out
 
         def enqueue_download(ws):
@@ -410,9 +426,14 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
         e2e_res = e2e_run(args.steps)
         fence()
         e2e_s = time.perf_counter() - t0
+        if trace is not None:
+            print("e2e host trace (ms per step):", {k: round(1e3 * v / (args.steps + min(args.warmup, 2)), 3)
+                                                    for k, v in trace.items()}, file=sys.stderr)
         sampler.window(time.time() - e2e_s, time.time())
         last = sets[(args.steps - 1) & 1]
         e2e = {"events": sum(r.events for r in e2e_res), "seconds": e2e_s, "h2d": h2d,
+               "hist_ms": sum(r.kernel_ns for r in e2e_res) / 1e6 / args.steps,
+               "sort_ms": sum(r.sort_ns for r in e2e_res) / 1e6 / args.steps,
                "d2h": d2h, "tally_sum": float(last.out_tally.sum()),
                "live_out": int((last.out_bank["dead"] == 0).sum())}
 
@@ -491,6 +512,8 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
         line["e2e"] = {"value": e2e_events_all / e2e_seconds, "unit": UNIT,
                        "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                        "ms_per_step": 1e3 * e2e_seconds / args.steps,
+                       "history_kernel_ms_per_step": e2e["hist_ms"],
+                       "sort_phase_ms_per_step": e2e["sort_ms"],
                        "tally_sum": e2e["tally_sum"], "live_particles_out": e2e["live_out"],
                        "pipeline": "double-buffered: upload of step i+1 and download of step "
                                    "i-1 overlap the transport of step i"}

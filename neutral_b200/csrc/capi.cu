@@ -84,7 +84,8 @@ struct Context {
   SinCosTable* d_sct = nullptr;
   int opt_device_inject = 1;
   unsigned long long* d_totals = nullptr;
-  unsigned long long* h_totals = nullptr;  // pinned
+  unsigned long long* h_totals = nullptr;  // pinned, mapped
+  unsigned long long* h_totals_dev = nullptr;  // the same memory as the device addresses it
   cudaEvent_t ev_begin = nullptr, ev_mid = nullptr, ev_end = nullptr;  // phase timing
   // The density tile maps are only read by the event loop: they are staged on a side stream
   // beside the begin-step / sort kernels (fork after the previous history kernel, join
@@ -105,10 +106,18 @@ struct Context {
   Bank* pending_bank = nullptr;  // a step enqueued by solve_transport_2d, not yet finished
   uint64_t pending_launches0 = 0;
   bool l2_limit_set = false;
+  size_t l2_setaside = 0;
   // mesh extent, read once per (edgex, edgey) pair for the sort's history-length estimate
   const double* mesh_ex = nullptr;
   const double* mesh_ey = nullptr;
   double mesh_width = 1.0, mesh_height = 1.0;
+  struct MeshExtent {
+    const double* ex;
+    const double* ey;
+    int nx, ny;
+    double width, height;
+  };
+  std::vector<MeshExtent> mesh_cache;  // the last few (edgex, edgey) pairs seen
   uint64_t launches = 0;
   uint64_t last_stats[8] = {0};
   int opt_print = 1;
@@ -188,7 +197,8 @@ int ensure_ready() {
   CU_TRY(cudaMalloc(&g.d_sct, sizeof(SinCosTable)));
   CU_TRY(cudaMemcpy(g.d_sct, &kHostSinCosTable, sizeof(SinCosTable), cudaMemcpyHostToDevice));
   CU_TRY(cudaMalloc(&g.d_totals, sizeof(unsigned long long) * kTotCount));
-  CU_TRY(cudaMallocHost(&g.h_totals, sizeof(unsigned long long) * kTotCount));
+  CU_TRY(cudaHostAlloc(&g.h_totals, sizeof(unsigned long long) * kTotCount, cudaHostAllocMapped));
+  CU_TRY(cudaHostGetDevicePointer(&g.h_totals_dev, g.h_totals, 0));
   CU_TRY(cudaEventCreate(&g.ev_begin));
   CU_TRY(cudaEventCreate(&g.ev_mid));
   CU_TRY(cudaEventCreate(&g.ev_end));
@@ -309,9 +319,34 @@ void upload_host_soa(const SoaView& host, int count, BankView& dst) {
 
 // Looks at the two energy grids once per (pointer, size) pair: are they the same grid, and
 // which leading bits spread their keys over the bucket index.
+// A host that alternates between a few working sets (bench.py's double-buffered e2e pipeline)
+// shows a few pairs in turn: the last kTableCacheSlots are remembered, so that no timestep of
+// a known pair issues a device-to-host copy - which would queue behind whatever bulk download
+// the host has in flight on the same copy engine.
+struct InspectedTables {
+  const double* s_keys;
+  const double* a_keys;
+  int s_n, a_n, same;
+  CsParams s_par, a_par;
+};
+constexpr size_t kTableCacheSlots = 8;
+std::vector<InspectedTables> g_table_cache;
+
 int inspect_tables(const double* s_keys, int s_n, const double* a_keys, int a_n) {
   if (g.cs_s_keys == s_keys && g.cs_a_keys == a_keys && g.cs_n == s_n && g.cs_a_n == a_n)
     return g.cs_same;
+  for (const InspectedTables& t : g_table_cache) {
+    if (t.s_keys == s_keys && t.a_keys == a_keys && t.s_n == s_n && t.a_n == a_n) {
+      g.cs_s_keys = s_keys;
+      g.cs_a_keys = a_keys;
+      g.cs_n = s_n;
+      g.cs_a_n = a_n;
+      g.cs_same = t.same;
+      g.cs_s_par = t.s_par;
+      g.cs_a_par = t.a_par;
+      return g.cs_same;
+    }
+  }
   std::vector<double> hs(std::max(s_n, 1)), ha(std::max(a_n, 1));
   CU_FATAL(cudaMemcpyAsync(hs.data(), s_keys, sizeof(double) * s_n, cudaMemcpyDeviceToHost,
                            g.stream));
@@ -325,7 +360,18 @@ int inspect_tables(const double* s_keys, int s_n, const double* a_keys, int a_n)
   g.cs_same = s_n == a_n && memcmp(hs.data(), ha.data(), sizeof(double) * s_n) == 0;
   g.cs_s_par = cs_params_from_host(hs.data(), s_n);
   g.cs_a_par = cs_params_from_host(ha.data(), a_n);
+  if (g_table_cache.size() >= kTableCacheSlots) g_table_cache.erase(g_table_cache.begin());
+  g_table_cache.push_back({s_keys, a_keys, s_n, a_n, g.cs_same, g.cs_s_par, g.cs_a_par});
   return g.cs_same;
+}
+
+// The step totals reach the host through mapped pinned memory, written by the device itself:
+// a cudaMemcpyAsync would wait its turn on the device-to-host copy engine behind any bulk
+// download the caller has in flight (measured: 3.4 ms per deck run in bench.py's e2e loop).
+__global__ void k_publish_totals(const unsigned long long* __restrict__ totals,
+                                 volatile unsigned long long* host_totals) {
+  if (threadIdx.x < kTotCount) host_totals[threadIdx.x] = totals[threadIdx.x];
+  __threadfence_system();
 }
 
 // Restages both tables into the library's own block (stage.cu) and fills the views.
@@ -408,19 +454,37 @@ void run_step(Bank* bank, int nx, int ny, uint64_t master_key, double dt, int nt
   CU_FATAL(cudaEventRecord(g.ev_begin, g.stream));
   if (g.opt_pipeline) {
     if (g.mesh_ex != edgex || g.mesh_ey != edgey) {  // extent of the mesh (a scheduling hint)
-      double ex[2], ey[2];
-      CU_FATAL(cudaMemcpyAsync(&ex[0], edgex, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-      CU_FATAL(cudaMemcpyAsync(&ex[1], edgex + nx, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-      CU_FATAL(cudaMemcpyAsync(&ey[0], edgey, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-      CU_FATAL(cudaMemcpyAsync(&ey[1], edgey + ny, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-      CU_FATAL(cudaStreamSynchronize(g.stream));
+      bool known = false;
+      for (const auto& m : g.mesh_cache)
+        if (m.ex == edgex && m.ey == edgey && m.nx == nx && m.ny == ny) {
+          g.mesh_width = m.width;
+          g.mesh_height = m.height;
+          known = true;
+        }
+      if (!known) {
+        double ex[2], ey[2];
+        CU_FATAL(cudaMemcpyAsync(&ex[0], edgex, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+        CU_FATAL(cudaMemcpyAsync(&ex[1], edgex + nx, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+        CU_FATAL(cudaMemcpyAsync(&ey[0], edgey, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+        CU_FATAL(cudaMemcpyAsync(&ey[1], edgey + ny, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+        CU_FATAL(cudaStreamSynchronize(g.stream));
+        g.mesh_width = ex[1] > ex[0] ? ex[1] - ex[0] : 1.0;
+        g.mesh_height = ey[1] > ey[0] ? ey[1] - ey[0] : 1.0;
+        if (g.mesh_cache.size() >= 8) g.mesh_cache.erase(g.mesh_cache.begin());
+        g.mesh_cache.push_back({edgex, edgey, nx, ny, g.mesh_width, g.mesh_height});
+      }
       g.mesh_ex = edgex;
       g.mesh_ey = edgey;
-      g.mesh_width = ex[1] > ex[0] ? ex[1] - ex[0] : 1.0;
-      g.mesh_height = ey[1] > ey[0] ? ey[1] - ey[0] : 1.0;
     }
     if (g.opt_l2_persist && !g.l2_limit_set) {  // set-aside for the persisting window
-      CU_FATAL(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 4u << 20));
+      size_t want = 4u << 20;
+      if (g.opt_l2_persist == 2) {  // experiment: persist (part of) the tally instead
+        int max_bytes = 0;
+        CU_FATAL(cudaDeviceGetAttribute(&max_bytes, cudaDevAttrMaxPersistingL2CacheSize, g.device));
+        want = (size_t)max_bytes;
+      }
+      CU_FATAL(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+      CU_FATAL(cudaDeviceGetLimit(&g.l2_setaside, cudaLimitPersistingL2CacheSize));
       g.l2_limit_set = true;
     }
     // P0: restage the read-only inputs (cross-section tables, density tile map)
@@ -469,7 +533,11 @@ void run_step(Bank* bank, int nx, int ny, uint64_t master_key, double dt, int nt
     // P4: event loop over the sorted live prefix
     g.launches += launch_history(a, g.d_n_live, s.n_upper, g.opt_fast_div != 0,
                                  g.opt_tally_prereduce != 0,
-                                 g.opt_l2_persist ? g.d_cs_stage : nullptr, g.cs_stage_bytes,
+                                 g.opt_l2_persist == 2 ? (const void*)tally
+                                 : g.opt_l2_persist   ? (const void*)g.d_cs_stage : nullptr,
+                                 g.opt_l2_persist == 2 ? sizeof(double) * (size_t)nx * ny
+                                                       : g.cs_stage_bytes,
+                                 g.opt_l2_persist == 2 ? g.l2_setaside : 0,
                                  g.opt_history_smem_pad, g.stream);
   } else {
     CU_FATAL(cudaEventRecord(g.ev_mid, g.stream));
@@ -477,8 +545,8 @@ void run_step(Bank* bank, int nx, int ny, uint64_t master_key, double dt, int nt
   }
   CU_FATAL(cudaGetLastError());
   CU_FATAL(cudaEventRecord(g.ev_end, g.stream));
-  CU_FATAL(cudaMemcpyAsync(g.h_totals, g.d_totals, sizeof(unsigned long long) * kTotCount,
-                           cudaMemcpyDeviceToHost, g.stream));
+  k_publish_totals<<<1, 32, 0, g.stream>>>(g.d_totals, g.h_totals_dev);
+  g.launches += 1;
   g.pending_bank = bank;
   g.pending_launches0 = launches0;
   // "defer_finish": the caller overlaps its own host work (launching the collective that

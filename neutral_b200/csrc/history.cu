@@ -338,8 +338,8 @@ static inline int blocks_for(int n, int threads) { return (n + threads - 1) / th
 // access-policy window that keeps it persisting in L2 (north_star phase 3), while the rest of
 // the kernel's traffic - the tally atomics above all - streams through the remainder.
 int launch_history(const StepArgs& a, const unsigned* n_live, int n_upper, bool fast_div,
-                   bool prereduce, const void* pin, size_t pin_bytes, int smem_pad,
-                   cudaStream_t st) {
+                   bool prereduce, const void* pin, size_t pin_bytes, size_t pin_budget,
+                   int smem_pad, cudaStream_t st) {
   if (n_upper <= 0) return 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(blocks_for(n_upper, kHistoryThreads));
@@ -362,7 +362,9 @@ int launch_history(const StepArgs& a, const unsigned* n_live, int n_upper, bool 
     attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
     attr[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(pin);
     attr[0].val.accessPolicyWindow.num_bytes = pin_bytes;
-    attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+    // a window larger than the set-aside persists a random `hitRatio` share of its lines
+    attr[0].val.accessPolicyWindow.hitRatio =
+        pin_budget && pin_bytes > pin_budget ? (float)((double)pin_budget / (double)pin_bytes) : 1.0f;
     attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     cfg.attrs = attr;

@@ -15,8 +15,8 @@ int launch_history_direct(const StepArgs& a, cudaStream_t st);
 int launch_sort_phase(const StepArgs& a, const SortArgs& s, const BankView& alt,
                       cudaStream_t st);
 int launch_history(const StepArgs& a, const unsigned* n_live, int n_upper, bool fast_div,
-                   bool prereduce, const void* pin, size_t pin_bytes, int smem_pad,
-                   cudaStream_t st);
+                   bool prereduce, const void* pin, size_t pin_bytes, size_t pin_budget,
+                   int smem_pad, cudaStream_t st);
 // Per-step staging of the read-only inputs (stage.cu).
 int launch_stage_cs(const double* keys, const double* vals, int n, double2* kv, int* bucket,
                     unsigned long long bits0, int shift, int nb, const double* twin_keys,
