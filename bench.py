@@ -252,6 +252,8 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries the one JSON line: NCCL's own banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = load_library(build=False)
     lib.initialise_devices.restype = None

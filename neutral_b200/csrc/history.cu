@@ -50,8 +50,13 @@ struct Parked {
   unsigned nc[kHistoryThreads];  // collisions so far this step = the RNG counter state
 };
 
+#ifdef NB_HISTORY_MAXNREG  // experiments: cap the registers directly instead of through min blocks
+#define NB_HISTORY_BOUNDS __maxnreg__(NB_HISTORY_MAXNREG)
+#else
+#define NB_HISTORY_BOUNDS __launch_bounds__(kHistoryThreads, NB_HISTORY_MIN_BLOCKS)
+#endif
 template <bool kFastDiv, bool kPreReduce>
-__global__ void __launch_bounds__(kHistoryThreads, NB_HISTORY_MIN_BLOCKS)
+__global__ void NB_HISTORY_BOUNDS
 k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
 #if NB_PARK_SMEM
   __shared__ Parked park;

@@ -5,7 +5,12 @@
 
 namespace nb {
 
-constexpr int kHistoryThreads = 128;
+// Threads per CTA of the history kernels. The register file holds 25 warps of 80 registers
+// (65536 / 2560): 6 CTAs of 128 threads use 24 of them, 5 CTAs of 160 threads all 25.
+#ifndef NB_HISTORY_THREADS
+#define NB_HISTORY_THREADS 128
+#endif
+constexpr int kHistoryThreads = NB_HISTORY_THREADS;
 
 // Every launch_* returns the number of kernels it launched (for the launch counter).
 int launch_history_direct(const StepArgs& a, cudaStream_t st);
