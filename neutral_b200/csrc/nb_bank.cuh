@@ -68,12 +68,15 @@ struct CsStage {
 
 // Density tile maps, rebuilt every timestep (stage.cu). fine[t] holds the density of the
 // 16x16-cell tile t when all its cells carry the same bit pattern, else the kMixedTileBits
-// marker; coarse[] is the same over 128x128-cell tiles (uniform iff its fine tiles are
+// marker; coarse[] is the same over 256x256-cell tiles (uniform iff its fine tiles are
 // uniform and equal). A facet crossing inside a uniform coarse tile needs no memory access at
-// all; the 8 KB coarse map stays L1-resident, the fine map L2-resident, and only mixed fine
+// all; the 2 KB coarse map stays L1-resident, the fine map L2-resident, and only mixed fine
 // tiles read the density mesh itself.
 constexpr int kTileShift = 4;
-constexpr int kCoarseShift = 7;
+#ifndef NB_COARSE_SHIFT
+#define NB_COARSE_SHIFT 8
+#endif
+constexpr int kCoarseShift = NB_COARSE_SHIFT;
 constexpr unsigned long long kMixedTileBits = 0x7ff8b200dead0001ull;  // a NaN payload of ours
 struct TileMap {
   const double* fine;

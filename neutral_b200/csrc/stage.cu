@@ -10,7 +10,7 @@
 //                  reference's search (omp3/neutral.c:506-511) by 1-6 probes of one or two
 //                  cache lines. Also checks what the host assumed about the tables.
 //   k_stage_tiles  one density value per uniform 16x16-cell tile and, from those
-//   k_stage_coarse (k_stage_coarse), per uniform 64x64-cell tile (TileMap): a facet crossing
+//   k_stage_coarse (k_stage_coarse), per uniform 256x256-cell tile (TileMap): a facet crossing
 //                  (omp3/neutral.c:372-378) consults the cache-resident maps instead of a
 //                  random 32-byte sector of the 128 MB density mesh.
 //

@@ -31,11 +31,16 @@ def _hashes(bank):
 MODES = {
     "pipeline": dict(pipeline=1, fast_div=1, tile_shift=9, length_bins=512),   # the default
     "pipeline-ieee-div": dict(pipeline=1, fast_div=0, tile_shift=2, length_bins=16),
-    "pipeline-class-only": dict(pipeline=1, fast_div=1, tile_shift=-1, length_bins=1),
+    # ... staging on the main stream, occupancy probe's shared-memory padding
+    "pipeline-class-only": dict(pipeline=1, fast_div=1, tile_shift=-1, length_bins=1,
+                                stage_overlap=0, history_smem_pad=4096),
     "pipeline-prereduce": dict(pipeline=1, fast_div=1, tile_shift=9, length_bins=512,
                                tally_prereduce=1),
     "direct": dict(pipeline=0, fast_div=0, tile_shift=9, length_bins=512),
 }
+
+
+DEFAULTS = dict(MODES["pipeline"], tally_prereduce=0, stage_overlap=1, history_smem_pad=0)
 
 
 @pytest.fixture(params=list(MODES))
@@ -45,7 +50,7 @@ def mode(request, gpu_lib):
     for k, v in opts.items():
         assert gpu_lib.nb200_set_option(k.encode(), v) >= -1
     yield request.param
-    for k, v in dict(MODES["pipeline"], tally_prereduce=0).items():
+    for k, v in DEFAULTS.items():
         gpu_lib.nb200_set_option(k.encode(), v)
 
 

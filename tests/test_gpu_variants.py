@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from neutral_b200.host import Simulation
-from test_gpu_parity import MODES, tally_close
+from test_gpu_parity import DEFAULTS, MODES, tally_close
 from variants import VARIANTS
 
 pytestmark = pytest.mark.gpu
@@ -37,5 +37,5 @@ def test_variant_matches_oracle_every_step(gpu_lib, port, name, config):
             assert tally_close(sim.tally_to_host(), tally), f"step {tt}: tally"
         sim.free()
     finally:
-        for k, v in dict(MODES["pipeline"], tally_prereduce=0).items():
+        for k, v in DEFAULTS.items():
             gpu_lib.nb200_set_option(k.encode(), v)

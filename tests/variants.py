@@ -69,7 +69,7 @@ def rect_stretched() -> Problem:
 
 
 def multi_tile() -> Problem:
-    """400 x 300 uniform cells: several coarse (128-cell) and fine (16-cell) tiles of the
+    """400 x 300 uniform cells: several coarse (256-cell) and fine (16-cell) tiles of the
     density maps, with boxes that straddle both kinds of tile border."""
     deck = Deck(path="multi_tile.params", nx=400, ny=300, dt=1.0e-7, iterations=3,
                 nparticles=5000, initial_energy=1.0e5,
