@@ -140,17 +140,28 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
         double e_next = __ldg((x_facet ? a.edgex : a.edgey) + (reflect ? c : cn) + (up_next ? 1 : 0));
         nf++;
         double q_mfp, q_dtc;
-        if (kFastDiv && (flags & kFlagInvStale)) {  // first facet after a collision / new density
-          flags &= ~(kFlagInvStale | kFlagDivOk);
-          if (fm_safe(v) & fm_safe(d.cell_mfp)) {  // both reciprocals side by side
-            v_inv = rcp_core(v);
-            d.cell_mfp_inv = rcp_core(d.cell_mfp);
-            flags |= kFlagDivOk;
-          } else {
-            v_inv = 1.0 / v;
-            d.cell_mfp_inv = 1.0 / d.cell_mfp;
-            if (safe_exponent(v)) flags |= kFlagSpeedOk;
-            if (safe_exponent(d.cell_mfp)) flags |= kFlagCellMfpOk;
+        if (flags & (kFlagInvStale | kFlagPending)) {  // first facet after a collision / new density
+          if (flags & kFlagPending) {
+            // :222-225 accumulates the deposits of consecutive collisions and :321-327 flushes
+            // them with this facet's own; here they go to the same cell as a reduction of
+            // their own (the tally's tolerance covers the different rounding of the sum), which
+            // keeps the parked slot out of the per-facet code
+            tally_add<kPreReduce>(a.tally, NB_CELL, PARKED(edep) * a.inv_ntotal);
+            PARKED(edep) = 0.0;
+            flags &= ~kFlagPending;
+          }
+          if (kFastDiv && (flags & kFlagInvStale)) {
+            flags &= ~(kFlagInvStale | kFlagDivOk);
+            if (fm_safe(v) & fm_safe(d.cell_mfp)) {  // both reciprocals side by side
+              v_inv = rcp_core(v);
+              d.cell_mfp_inv = rcp_core(d.cell_mfp);
+              flags |= kFlagDivOk;
+            } else {
+              v_inv = 1.0 / v;
+              d.cell_mfp_inv = 1.0 / d.cell_mfp;
+              if (safe_exponent(v)) flags |= kFlagSpeedOk;
+              if (safe_exponent(d.cell_mfp)) flags |= kFlagCellMfpOk;
+            }
           }
         }
         if (kFastDiv && (flags & kFlagDivOk) == kFlagDivOk && safe_exponent(d_facet)) {
@@ -163,12 +174,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
         mfp -= q_mfp;
         dtc -= q_dtc;
         // :321-327 - deposit, flush to the tally (update_tallies, :408-420), reset
-        double edep = deposition(w, d_facet, d.stb, d.heat, nd);
-        if (flags & kFlagPending) {
-          edep = PARKED(edep) + edep;
-          PARKED(edep) = 0.0;
-          flags &= ~kFlagPending;
-        }
+        const double edep = deposition(w, d_facet, d.stb, d.heat, nd);
         tally_add<kPreReduce>(a.tally, NB_CELL, edep * a.inv_ntotal);
         x += d_facet * ox;
         y += d_facet * oy;
