@@ -137,6 +137,8 @@ struct Context {
   size_t cs_stage_bytes = 0;
   double* d_tile_rho = nullptr;
   int tile_capacity = 0;
+  double* d_edges4 = nullptr;
+  int edges_capacity = 0;
   std::string last_error;
 };
 
@@ -410,6 +412,16 @@ void stage_tiles(StepArgs& a, cudaStream_t st) {
   }
   g.launches += launch_stage_tiles(a.density, a.nx, a.ny, g.d_tile_rho, g.d_tile_rho + nfine,
                                    &a.tiles, st);
+  // ... and the target-edge rows (same consumer: the event loop only)
+  const int stride = ((std::max(a.nx, a.ny) + 1 + 31) / 32) * 32;
+  if (g.edges_capacity < 4 * stride) {
+    cudaFree(g.d_edges4);
+    CU_FATAL(cudaMalloc(&g.d_edges4, sizeof(double) * 4 * (size_t)stride));
+    g.edges_capacity = 4 * stride;
+  }
+  g.launches += launch_stage_edges(a.edgex, a.nx, a.edgey, a.ny, stride, g.d_edges4, st);
+  a.edges4 = g.d_edges4;
+  a.edge_stride = stride;
 }
 
 void finish_step(uint64_t* facet_events, uint64_t* collision_events);

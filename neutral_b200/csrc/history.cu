@@ -137,7 +137,11 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
         const int cn = c + s;
         const bool reflect = (unsigned)cn >= (unsigned)(x_facet ? a.nx : a.ny);
         const bool up_next = (reflect ? -s : s) >= 0;
-        double e_next = __ldg((x_facet ? a.edgex : a.edgey) + (reflect ? c : cn) + (up_next ? 1 : 0));
+        // next target edge from the staged rows: [axis] for the far edge, [2 + axis] for the
+        // near edge with the open-bound correction already applied (:442-444, 448-450)
+        const int e_row = (x_facet ? 0 : 1) + (up_next ? 0 : 2);
+        const int e_at = e_row * a.edge_stride + (reflect ? c : cn) + (up_next ? 1 : 0);
+        double e_next = __ldg(a.edges4 + e_at);
         nf++;
         double q_mfp, q_dtc;
         if (flags & (kFlagInvStale | kFlagPending)) {  // first facet after a collision / new density
@@ -180,7 +184,6 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
         y += d_facet * oy;
         // the edge load is consumed here, after the arithmetic it overlapped with
         asm volatile("" : "+d"(e_next));
-        if (!up_next) e_next -= kOpenBoundCorrection;
         if (x_facet) ex = e_next; else ey = e_next;
         if (reflect) {
           if (x_facet) { ox = -ox; uxi = -uxi; } else { oy = -oy; uyi = -uyi; }

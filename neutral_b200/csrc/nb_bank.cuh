@@ -113,6 +113,14 @@ struct StepArgs {
   // staged per-step copies (stage.cu); kernels that do not use them ignore the fields
   CsStage cs_s, cs_a;
   TileMap tiles;
+  // Target edges of a facet crossing, restaged per step as four rows of `edge_stride` doubles:
+  // row 0 = edgex, row 1 = edgey (the far edge of a cell for a direction component >= 0), rows
+  // 2, 3 = the same minus OPEN_BOUND_CORRECTION (the near edge pulled in, omp3/neutral.c:443,
+  // 449 - the subtraction is done once per edge instead of once per facet, same operands,
+  // same bits). One base pointer and an integer row select replace two pointer selects and
+  // the per-facet correction.
+  const double* edges4;
+  int edge_stride;
 };
 
 // Scratch of the per-step counting sort (pipeline.cu).

@@ -102,6 +102,23 @@ __global__ void __launch_bounds__(256) k_stage_coarse(const double* __restrict__
   coarse[t] = bits_to_double(same ? first : kMixedTileBits);
 }
 
+// Rows 0..3 of StepArgs::edges4 (see nb_bank.cuh).
+__global__ void __launch_bounds__(256) k_stage_edges(const double* __restrict__ edgex, int nx,
+                                                     const double* __restrict__ edgey, int ny,
+                                                     int stride, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= nx) {
+    const double e = edgex[i];
+    out[i] = e;
+    out[2 * (size_t)stride + i] = e - kOpenBoundCorrection;
+  }
+  if (i <= ny) {
+    const double e = edgey[i];
+    out[(size_t)stride + i] = e;
+    out[3 * (size_t)stride + i] = e - kOpenBoundCorrection;
+  }
+}
+
 static inline int blocks_for(size_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
 int launch_stage_cs(const double* keys, const double* vals, int n, double2* kv, int* bucket,
@@ -110,6 +127,13 @@ int launch_stage_cs(const double* keys, const double* vals, int n, double2* kv, 
   if (n <= 0) return 0;
   k_stage_cs<<<blocks_for((size_t)(n > nb + 1 ? n : nb + 1), 256), 256, 0, st>>>(keys, vals, n, kv, bucket, bits0, shift, nb,
                                                  twin_keys, totals);
+  return 1;
+}
+
+int launch_stage_edges(const double* edgex, int nx, const double* edgey, int ny, int stride,
+                       double* out, cudaStream_t st) {
+  const int n = (nx > ny ? nx : ny) + 1;
+  k_stage_edges<<<blocks_for((size_t)n, 256), 256, 0, st>>>(edgex, nx, edgey, ny, stride, out);
   return 1;
 }
 

@@ -29,6 +29,9 @@ int launch_stage_cs(const double* keys, const double* vals, int n, double2* kv, 
 // fine/coarse must hold tile_counts(nx, ny) doubles; *map receives the views.
 int launch_stage_tiles(const double* density, int nx, int ny, double* fine, double* coarse,
                        TileMap* map, cudaStream_t st);
+// out must hold 4 * stride doubles, stride >= max(nx, ny) + 1.
+int launch_stage_edges(const double* edgex, int nx, const double* edgey, int ny, int stride,
+                       double* out, cudaStream_t st);
 int launch_selftest_div(const double* a, const double* b, double* fast, double* ieee, int n,
                         cudaStream_t st);
 int launch_selftest_fastmath(const double* a, const double* b, double* out, int n,
