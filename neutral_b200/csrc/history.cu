@@ -154,21 +154,20 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
             PARKED(edep) = 0.0;
             flags &= ~kFlagPending;
           }
+          if (!kFastDiv) flags &= ~kFlagInvStale;  // no reciprocals to refresh in this variant
           if (kFastDiv && (flags & kFlagInvStale)) {
-            flags &= ~(kFlagInvStale | kFlagDivOk);
+            flags &= ~kFlagInvStale;
             if (fm_safe(v) & fm_safe(d.cell_mfp)) {  // both reciprocals side by side
               v_inv = rcp_core(v);
               d.cell_mfp_inv = rcp_core(d.cell_mfp);
-              flags |= kFlagDivOk;
-            } else {
-              v_inv = 1.0 / v;
-              d.cell_mfp_inv = 1.0 / d.cell_mfp;
-              if (safe_exponent(v)) flags |= kFlagSpeedOk;
-              if (safe_exponent(d.cell_mfp)) flags |= kFlagCellMfpOk;
-            }
+              flags &= ~kFlagDivBad;
+            }  // else: kFlagDivBad stays set and every facet takes the plain divisions
           }
         }
-        if (kFastDiv && (flags & kFlagDivOk) == kFlagDivOk && safe_exponent(d_facet)) {
+        // 2^-255 <= d_facet < 2^257 and both reciprocals valid, as one range test: the flag is the
+        // top bit, a negative or NaN dividend has it set too
+        const unsigned div_key = (unsigned)__double2hiint(d_facet) | (flags & kFlagDivBad);
+        if (kFastDiv && div_key - 0x30000000u < 0x20000000u) {
           q_mfp = div_by_known_unchecked(d_facet, d.cell_mfp, d.cell_mfp_inv);
           q_dtc = div_by_known_unchecked(d_facet, v, v_inv);
         } else {
@@ -283,7 +282,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
               PARKED(e) = e_new;
               PARKED(Sig_s) = S_s;
               PARKED(p_absorb) = pa;
-              flags = (flags & ~(kFlagSpeedOk | kFlagCellMfpOk)) | kFlagInvStale;
+              flags |= kFlagInvStale | kFlagDivBad;
             } else {
               ox = PARKED(Sig_s);
               oy = PARKED(p_absorb);
@@ -305,7 +304,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
             PARKED(e) = e_new;
             derive(a, e_new, nd, d, PARKED(Sig_s), PARKED(p_absorb), flags);
             v = kFastDiv ? speed_of_fast(e_new) : speed_of(e_new);
-            flags = (flags & ~kFlagSpeedOk) | kFlagInvStale;  // v_inv is recomputed on demand
+            flags |= kFlagInvStale | kFlagDivBad;  // v_inv is recomputed on demand
             uxi = 1.0 / (ox * v);
             uyi = 1.0 / (oy * v);
             ex = target_edge(a.edgex, cx, axis_step(ox));

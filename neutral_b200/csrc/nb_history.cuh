@@ -21,9 +21,10 @@ __device__ __forceinline__ double fine_value(const StepArgs& a, int cx, int cy) 
 
 // Per-particle flag bits kept in one register.
 enum : unsigned {
-  kFlagSpeedOk = 1u,      // the speed is inside the proven range of div_by_known
-  kFlagCellMfpOk = 2u,    // so is the cell mean free path
-  kFlagDivOk = kFlagSpeedOk | kFlagCellMfpOk,
+  // The two reciprocals a facet divides through (1 / speed, 1 / cell mean free path) are NOT
+  // both valid: stale, or a divisor outside the proven range of div_by_known. The top bit, so
+  // that one OR folds it into the range test of the dividend (history.cu).
+  kFlagDivBad = 0x80000000u,
   kFlagInvStale = 64u,    // the two reciprocals have not been recomputed since their divisors
                           // changed: collision chains never need them, the next facet does
   kFlagCoarseMixed = 4u,  // the current coarse tile is not uniform: consult the fine map
@@ -76,7 +77,7 @@ __device__ __forceinline__ void derive(const StepArgs& a, double e, double nd, D
     p_absorb = S_a / S_t;
   }
   d.cell_mfp = 1.0 / S_t;
-  flags = (flags & ~kFlagCellMfpOk) | kFlagInvStale;  // cell_mfp_inv is recomputed on demand
+  flags |= kFlagInvStale | kFlagDivBad;  // cell_mfp_inv is recomputed on demand
 }
 
 // Direction of travel along one axis as a cell step: +1, -1, or 0 for a component that is
