@@ -136,11 +136,19 @@ def reference_rate(deck_name: str, target_seconds: float, steps: int = 1, warmup
     from oracle.oracle import OraclePort, ReferenceOmp3
 
     cores = len(os.sched_getaffinity(0))
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    # All the host threads the box has, whatever the launcher exported: torchrun sets
+    # OMP_NUM_THREADS=1 for its workers, which would time the reference on one core while
+    # reporting sixteen. NB200_REF_THREADS overrides.
+    cores = int(os.environ.get("NB200_REF_THREADS", cores))
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     os.environ.setdefault("OMP_PROC_BIND", "close")
     os.environ.setdefault("OMP_PLACES", "cores")
     kind = "reference" if ReferenceOmp3.available() else "port"
     eng = ReferenceOmp3() if kind == "reference" else OraclePort()
+    try:  # the OpenMP runtime may have read the environment before this point (torch loads one)
+        C.CDLL("libgomp.so.1").omp_set_num_threads(cores)
+    except OSError:
+        pass
     deck = load_deck(deck_name)
 
     def run_once(nparticles):
@@ -252,8 +260,9 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
 
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # stdout carries the one JSON line: NCCL's own banner / debug output goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries the one JSON line: keep NCCL's version banner off it
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = load_library(build=False)
     lib.initialise_devices.restype = None
