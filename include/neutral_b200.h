@@ -207,7 +207,11 @@ int nb200_accumulate_clear_async(double* dst_device, double* src_device, size_t 
  * "length_bins" (bins of expected history length in the sort key, default 512; <= 1: none);
  * "tally_prereduce" (1: combine same-cell tally flushes of a warp with shuffles before the
  * atomic; default 0); "l2_persist" (1: the history kernel's launch carries an access-policy
- * window that keeps the staged cross-section tables persisting in L2; default 0).
+ * window that keeps the staged cross-section tables persisting in L2; 2: a window over the
+ * tally instead, measured slower; default 0); "stage_overlap" (1, default: the density tile
+ * maps and target-edge rows are staged on a side stream beside the sort phase); 
+ * "history_smem_pad" (bytes of unused dynamic shared memory per CTA of the history kernel:
+ * an occupancy / carve-out probe, default 0).
  * "device_inject" (1, default: inject_particles generates the bank on the device with the
  * bit-exact sin/cos of nb_sincos.cuh; 0: on the host with libm, then uploads it);
  * "defer_finish" (1: solve_transport_2d returns as soon as the timestep is enqueued on the

@@ -17,12 +17,19 @@
 //  * the cell step/reflect logic (:332-368) is computed on the crossed axis only, without
 //    the reference's four-way branch, so a warp does not serialise over directions;
 //  * the two edges a particle is heading for are carried in registers and only the crossed
-//    axis reloads its next edge - issued before the event's arithmetic, consumed after it;
+//    axis reloads its next edge - from the staged edge rows (far / near edge per axis, the
+//    open-bound correction pre-applied), issued before the event's arithmetic, consumed after;
 //  * the density of the entered cell comes from the per-step tile maps (stage.cu) unless the
 //    tile is mixed; cross sections come from the staged tables through the bucket index;
+//  * the elastic scatter (:262-297) is one basic block of branch-free division / reciprocal /
+//    square-root cores (nb_fastmath.cuh, nb_history.cuh) whenever its operands are in the
+//    range where those are the operators' own bits, so its independent chains interleave;
+//  * nothing that only collisions need is touched by a facet: energy deposited by collisions
+//    is flushed by the first facet after them (a rarely taken block), not folded into every
+//    facet's deposit.
 //
-// Compiled with -fmad=false: the only fused operations are the explicit fma() of nb_log and
-// div_by_known.
+// Compiled with -fmad=false: the only fused operations are the explicit fma() of nb_log,
+// div_by_known and the cores.
 #include "nb_history.cuh"
 
 namespace nb {
