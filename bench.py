@@ -511,7 +511,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
                                 f"{2 * ncells * 8 / 2**20:.0f} MiB, random access)",
                    "parallelism": f"particle-sharded x{world}, NCCL all-reduce of the tally "
                                   "delta per timestep" if world > 1 else "single GPU",
-                   "options": args.opts or "defaults (pipeline=1,fast_div=1,tile_shift=9,"
+                   "options": args.opts or "defaults (pipeline=1,fast_div=1,tile_shift=8,"
                                            "length_bins=512)",
                    "events_per_step": events_all / args.steps,
                    "tally_sum": tally_sum},

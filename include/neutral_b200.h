@@ -203,7 +203,7 @@ int nb200_accumulate_clear_async(double* dst_device, double* src_device, size_t 
  * phased timestep - begin-step/classify, counting sort by next-event type and tile, event
  * loop; 0: the direct one-thread-per-history kernel on the unsorted bank); "fast_div"
  * (1, default: exact division by loop-invariant divisors through their reciprocals);
- * "tile_shift" (log2 of the sort tile edge in cells, default 9; < 0: no spatial key);
+ * "tile_shift" (log2 of the sort tile edge in cells, default 8; < 0: no spatial key);
  * "length_bins" (bins of expected history length in the sort key, default 512; <= 1: none);
  * "tally_prereduce" (1: combine same-cell tally flushes of a warp with shuffles before the
  * atomic; default 0); "l2_persist" (1: the history kernel's launch carries an access-policy

@@ -98,7 +98,7 @@ struct Context {
   unsigned* d_n_live = nullptr;
   int bins_capacity = 0;
   int opt_fast_div = 1;
-  int opt_tile_shift = 9;
+  int opt_tile_shift = 8;
   int opt_length_bins = 512;
   int opt_tally_prereduce = 0;
   int opt_l2_persist = 0;

@@ -29,7 +29,7 @@ def _hashes(bank):
 
 
 MODES = {
-    "pipeline": dict(pipeline=1, fast_div=1, tile_shift=9, length_bins=512),   # the default
+    "pipeline": dict(pipeline=1, fast_div=1, tile_shift=8, length_bins=512),   # the default
     "pipeline-ieee-div": dict(pipeline=1, fast_div=0, tile_shift=2, length_bins=16),
     # ... staging on the main stream, occupancy probe's shared-memory padding
     "pipeline-class-only": dict(pipeline=1, fast_div=1, tile_shift=-1, length_bins=1,
