@@ -135,7 +135,16 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
       const double d_census = v * dtc;
       const bool collide = d_coll < d_facet && d_coll < d_census;
 
+#ifdef NB_PROBE_COLLISION_ONLY
+      // Compile-time probe for DESIGN.md 8 item 1 (never a product build): what the event loop
+      // needs in registers when it leaves at the first event that is not a collision.
+      //   NB200_DEFINES="-DNB_PROBE_COLLISION_ONLY -DNB_HISTORY_MIN_BLOCKS=7" NB200_LIB=probe.so \
+      //     python -m neutral_b200.build      ->  ptxas: 72 registers, 0 bytes of spills
+      if (!collide) break;
+      if (false) {
+#else
       if (!collide && d_facet < d_census) {
+#endif
         // ---- facet_event, :303-380
         // :332-368 on the crossed axis only: step one cell, or reflect at the mesh boundary.
         // Decided first so that the next target edge is in flight during the arithmetic.
