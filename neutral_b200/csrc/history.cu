@@ -136,8 +136,9 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
       const bool collide = d_coll < d_facet && d_coll < d_census;
 
 #ifdef NB_PROBE_COLLISION_ONLY
-      // Compile-time probe for DESIGN.md 8 item 1 (never a product build): what the event loop
-      // needs in registers when it leaves at the first event that is not a collision.
+      // Compile-time probe (never a product build): what the event loop needs in registers
+      // when it leaves at the first event that is not a collision. The kernel built on it was
+      // measured and rejected, profiles/r01/experiments/session4/collide_kernel_variant.diff.
       //   NB200_DEFINES="-DNB_PROBE_COLLISION_ONLY -DNB_HISTORY_MIN_BLOCKS=7" NB200_LIB=probe.so \
       //     python -m neutral_b200.build      ->  ptxas: 72 registers, 0 bytes of spills
       if (!collide) break;
