@@ -16,7 +16,7 @@
  * to, or without, the reference's neutral_data.h.
  *
  * Memory spaces. In the device-resident flavour (section 1) every array argument is DEVICE
- * memory on the current GPU, obtained from the allocation layer (section 2) or from any
+ * memory on the current GPU (the bank's primary GPU when the bank is sharded over several), obtained from the allocation layer (section 2) or from any
  * other CUDA allocator (e.g. a torch tensor's data_ptr); scalars passed by pointer
  * (nlocal_particles, facet_events, collision_events) and the CrossSection structs
  * themselves are HOST memory. Section 3 has the host-buffer flavour.
@@ -36,7 +36,12 @@
 extern "C" {
 #endif
 
-#define NB200_ABI_VERSION 1
+#define NB200_ABI_VERSION 2
+/* nb200_set_option / nb200_get_option / nb200_bank_set_option: unknown name or value out of
+ * range (option values themselves may be negative, e.g. tile_shift = -1). */
+#define NB200_BAD_OPTION (-2147483647 - 1)
+/* Bytes one rank contributes to nb200_mp_connect (CUDA IPC handle + NCCL id). */
+#define NB200_MP_BLOB_BYTES 256
 
 /* == reference `Particle` under -DSoA (neutral_data.h:48-61) */
 typedef struct {
@@ -77,7 +82,13 @@ typedef struct {
  * to, as omp3 does (omp3/neutral.c:202-203); prints "Particles  <n>" (omp3/neutral.c:205).
  * reduce_array0..2, when non-null, are uint64[bank size] device arrays that receive the
  * cumulative per-particle facet / collision / census counts in injection order.
- * pad must be 0 and x_off = y_off = 0 (the only configuration main.c:34,101-110 produces). */
+ * pad must be 0 and x_off = y_off = 0 (the only configuration main.c:34,101-110 produces).
+ *
+ * A bank sharded over several GPUs (NB200_NGPUS / option "ngpus", or a multi-process group,
+ * section 5) transports every shard on its own GPU against replicas of the read-only inputs
+ * and combines the tally inside the library (csrc/nb_group.cuh); the counts returned are the
+ * sums over the shards. The caller-visible tally is then brought up to date lazily: by
+ * validate, by copy_buffer / nb200_memcpy_d2h of it, or by nb200_tally_sync. */
 void solve_transport_2d(
     const int nx, const int ny, const int global_nx, const int global_ny,
     const uint64_t master_key, const int pad, const int x_off, const int y_off,
@@ -91,9 +102,16 @@ void solve_transport_2d(
 
 /* Creates and fills the bank. Replaces inject_particles (neutral_interface.h:23-31 /
  * omp3/neutral.c:560-630): positions, cells and directions come from the same
- * Threefry-2x64 streams and the same libm cos/sin as the reference, computed on the host
- * and uploaded. Returns the bytes of device memory allocated; *particles receives an
- * opaque handle whose first 11 members alias a plain SoA view (see nb200_bank_export). */
+ * Threefry-2x64 streams as the reference and from a bit-exact restatement of the libm cos/sin
+ * the reference calls, generated on the device(s) where the bank lives (option
+ * "device_inject" = 0: computed on the host with libm and uploaded; same bits).
+ * Returns the bytes of device memory allocated (including the head-room of option
+ * "headroom_pct"; omp3/neutral.c:570 allocates twice the bank). *particles receives an opaque
+ * handle laid out as the reference's -DSoA struct of 11 pointers (neutral_data.h:48-61).
+ * The pointers are NULL until something asks for them: nb200_bank_view / nb200_bank_export
+ * make them a plain DEVICE SoA view; with option "host_mirror" = 1 (or NB200_HOST_MIRROR=1 in
+ * the environment, for visit_dump decks: main.c:169-200 reads the bank on the host) they are
+ * HOST arrays that the library refreshes after inject and after every collected timestep. */
 size_t inject_particles(const int nparticles, const int global_nx, const int local_nx,
                         const int local_ny, const int pad,
                         const double local_particle_left_off,
@@ -104,8 +122,12 @@ size_t inject_particles(const int nparticles, const int global_nx, const int loc
                         const double* edgey, const double initial_energy,
                         nb200_particle_soa** particles);
 
-/* Sums the tally on the device and compares it with problems/neutral.tests at 1e-3.
- * Replaces validate (neutral_interface.h:35-36 / omp3/neutral.c:520-557); same printed lines. */
+/* Sums the tally on the device and compares it with problems/neutral.tests at 1e-3
+ * (relative: VALIDATE_TOLERANCE, neutral_data.h:27). Replaces validate
+ * (neutral_interface.h:35-36 / omp3/neutral.c:520-557); same printed lines. When the
+ * environment names a file in NB200_RESULTS_JSON the verdict is also written there as JSON:
+ * deck, tally total, expected value, relative error, PASSED / FAILED / NOT_VALIDATED and the
+ * per-timestep counts the library saw. */
 void validate(const int nx, const int ny, const char* params_filename, const int rank,
               double* energy_tally);
 
@@ -151,7 +173,8 @@ int nb200_abi_version(void);
 const char* nb200_last_error(void);
 /* Number of CUDA devices visible (0 = none: every compute entry point fails loudly). */
 int nb200_device_count(void);
-/* CUDA stream (cudaStream_t) all work is enqueued on; default 0 = the legacy default stream. */
+/* CUDA stream (cudaStream_t) all work of the CURRENT device is enqueued on; default 0 = the
+ * legacy default stream. Refused (-4) while timesteps are enqueued and not collected. */
 int nb200_set_stream(void* cuda_stream);
 
 /* Particle sharding across GPUs: the next inject_particles builds only global particles
@@ -178,7 +201,16 @@ int nb200_bank_import(nb200_particle_soa* particles);
 /* Overwrites the bank's state from another bank of the same size (device to device). */
 int nb200_bank_copy(nb200_particle_soa* dst, nb200_particle_soa* src);
 int nb200_bank_size(nb200_particle_soa* particles);
+/* Slots allocated (>= size: option "headroom_pct") and GPUs the bank is sharded over. */
+int nb200_bank_capacity(nb200_particle_soa* particles);
+int nb200_bank_gpus(nb200_particle_soa* particles);
+/* Appends `count` particles (host SoA arrays) into the bank's head-room: they become
+ * particles [size, size + count) in injection order with the next global indices as RNG keys.
+ * -5 when they do not fit. Single-GPU banks. */
+int nb200_bank_append(nb200_particle_soa* particles, const nb200_particle_soa* host, int count);
 int nb200_bank_free(nb200_particle_soa* particles);
+/* Bank operations that rewrite a bank (upload, import, copy, append, export, download) are
+ * refused with -4 while timesteps of it are enqueued and not collected (defer_finish). */
 
 /* Raw device/host copies for hosts without a CUDA binding of their own. */
 int nb200_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes);
@@ -216,13 +248,31 @@ int nb200_accumulate_clear_async(double* dst_device, double* src_device, size_t 
  * bit-exact sin/cos of nb_sincos.cuh; 0: on the host with libm, then uploads it);
  * "defer_finish" (1: solve_transport_2d returns as soon as the timestep is enqueued on the
  * stream; the counts are collected - and the reference's "Particles" line printed - by
- * nb200_solve_finish, which must be called before the next solve_transport_2d; default 0).
- * Returns the previous value, or a negative code for an unknown name. */
+ * nb200_solve_finish; up to 4 timesteps of a bank may be in flight, so a host can keep the
+ * GPU fed without a round trip per timestep; default 0).
+ * "ngpus" (GPUs the NEXT inject_particles / nb200_bank_create shards its bank over, starting
+ * with the current device; 0/1: one; environment NB200_NGPUS=<n>|all sets the default);
+ * "collective" (how a sharded run combines its tally: 1, default: the library's own
+ * peer-memory reduce-scatter kernel, csrc/nb_group.cuh; 0: NCCL reduce-scatter, bound at run
+ * time; environment NB200_COLLECTIVE=nccl); "reduce_ctas" (grid of that kernel);
+ * "host_mirror" (see inject_particles); "headroom_pct" (extra bank slots in percent).
+ * "tally_prereduce" = 1 implies "fast_div" = 1 (it has no separate IEEE-division build).
+ * Options are process-wide defaults; nb200_bank_set_option overrides one for one bank (the
+ * creation-time options ngpus / host_mirror / headroom_pct / device_inject apply when the bank
+ * is created). Returns the previous value, or NB200_BAD_OPTION for an unknown name or a value
+ * outside the option's range (nb200_last_error says which). */
 int nb200_set_option(const char* name, int value);
+int nb200_get_option(const char* name);
+int nb200_bank_set_option(nb200_particle_soa* particles, const char* name, int value);
 /* Completes a timestep enqueued under defer_finish=1: waits for the stream and ADDS the
  * step's counts to *facet_events / *collision_events (either may be null), like
  * omp3/neutral.c:202-203. */
 int nb200_solve_finish(uint64_t* facet_events, uint64_t* collision_events);
+/* The same for a named bank (nb200_solve_finish refers to the bank that enqueued last): collects
+ * the OLDEST pending timestep; nb200_bank_pending says how many are pending. */
+int nb200_bank_solve_finish(nb200_particle_soa* particles, uint64_t* facet_events,
+                            uint64_t* collision_events);
+int nb200_bank_pending(nb200_particle_soa* particles);
 
 /* Statistics of the most recent solve_transport_2d: out[0..4] = facets, collisions,
  * particles processed, census events, deaths; out[5] = kernels launched by that call;
@@ -231,6 +281,44 @@ int nb200_solve_finish(uint64_t* facet_events, uint64_t* collision_events);
 int nb200_last_step_stats(uint64_t out[8]);
 /* Kernels launched by this library since load (monotonic). */
 uint64_t nb200_kernel_launches(void);
+
+/* ------------------------------------------------------------------------------------
+ * 5. Particle-sharded runs. Histories are independent and keyed by the GLOBAL
+ *    particle index (omp3/neutral.c:632-641), so GPU g of G transports the contiguous range of
+ *    omp3's thread split (omp3/neutral.c:64-74) and only the additive tally is combined: each
+ *    GPU deposits a timestep into a private delta, and one library kernel per GPU reads its
+ *    slice of every peer's delta over NVLink and folds the sum into the slice of the
+ *    cumulative tally it owns (csrc/nb_group.cuh), beside the next timestep's transport.
+ *    Two ways to get there:
+ *      - one process, several GPUs: option "ngpus" / NB200_NGPUS before inject_particles.
+ *        Nothing else changes for the caller (this is how `NB200_NGPUS=8 ./neutral.b200 ...`
+ *        runs the reference's unmodified main.c on 8 GPUs);
+ *      - one process per GPU (torchrun, MPI): nb200_set_shard + nb200_mp_init on every rank,
+ *        exchange the blobs with whatever the host has (torch.distributed.all_gather, MPI),
+ *        nb200_mp_connect. From then on solve_transport_2d on that GPU takes part in the group.
+ * ---------------------------------------------------------------------------------- */
+/* Allocates this rank's part of the group for a tally of `ncells` doubles on the current GPU
+ * and writes NB200_MP_BLOB_BYTES bytes the peers need into blob_out. */
+int nb200_mp_init(int nranks, int rank, size_t ncells, void* blob_out);
+/* blobs = nranks * NB200_MP_BLOB_BYTES bytes, rank order. -7: a peer's memory cannot be mapped
+ * (no NVLink/PCIe peer path): finalize and retry with option "collective" = 0. */
+int nb200_mp_connect(const void* blobs);
+int nb200_mp_finalize(void);
+/* Brings the caller-visible tally up to date with everything the group has deposited
+ * (all-gather of the owned slices, added to the tally; NULL = every tracked tally).
+ * In a multi-process group this is a collective: every rank calls it, equally often. */
+int nb200_tally_sync(double* tally_device);
+/* The other GPUs of a single-process sharded bank work on replicas of the read-only inputs
+ * (density, edges, tables), made when a pointer is first seen: tell the library when the
+ * caller has changed such an array in place. */
+int nb200_update_replicas(void);
+
+/* What the history kernel is bound by on facet-dominated decks, measured in place: FP64
+ * reductions per second the L2 retires (csrc/microbench.cu; pattern 3 = the peak, 1 = a
+ * particle's mesh walk, 0 = random cells, 5 / 6 = 32 / 4 lanes on consecutive cells) into a
+ * footprint of footprint_bytes, `iters` reductions per thread on 2368 x 128 threads. */
+int nb200_microbench_red(int pattern, size_t footprint_bytes, int iters,
+                         double* reductions_per_s);
 
 /* Known-answer hooks on the bit-exact building blocks (device and host builds of the same
  * source). raw/unit/neglog hold 2n entries: Threefry-2x64-20(ctr={counter,0},

@@ -16,9 +16,10 @@ CSRC = os.path.join(HERE, "csrc")
 # NB200_LIB / NB200_DEFINES build and load an experiment variant next to the product library
 # (e.g. NB200_DEFINES=-DNB_HISTORY_MIN_BLOCKS=5 NB200_LIB=libneutral_b200.mb5.so).
 LIB = os.path.join(HERE, os.environ.get("NB200_LIB", "libneutral_b200.so"))
-SOURCES = ["transport.cu", "stage.cu", "pipeline.cu", "history.cu", "capi.cu"]
+SOURCES = ["transport.cu", "stage.cu", "pipeline.cu", "history.cu", "group.cu", "microbench.cu",
+           "capi.cu"]
 HEADERS = ["transport.cuh", "nb_device.cuh", "nb_bank.cuh", "nb_math.cuh", "nb_history.cuh",
-           "nb_sincos.cuh", "nb_fastmath.cuh", "glibc_log_table.inc", "glibc_sincos_table.inc",
+           "nb_sincos.cuh", "nb_fastmath.cuh", "nb_group.cuh", "nb_nccl_dyn.cuh", "engine.cuh", "glibc_log_table.inc", "glibc_sincos_table.inc",
            os.path.join("..", "..", "include", "neutral_b200.h")]
 
 NVCC_FLAGS = [
@@ -49,7 +50,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
     cmd = [find_nvcc()] + NVCC_FLAGS + os.environ.get("NB200_DEFINES", "").split() + ["-shared"] + \
-        [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB, "-lgomp"]
+        [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB, "-lgomp", "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(HERE, "build.log"), "w") as f:

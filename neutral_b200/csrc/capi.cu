@@ -1,23 +1,53 @@
 // capi.cu - the C ABI of libneutral_b200.so (declared in include/neutral_b200.h).
 //
-// Host-side glue only: argument checking, device memory, stream ordering, counters. The
-// arithmetic of the hot path lives in transport.cu. There is deliberately no CPU fallback:
+// Host-side glue only: argument checking, device memory, stream ordering, counters, the
+// multi-GPU orchestration. The arithmetic of the hot path lives in the kernels (history.cu,
+// pipeline.cu, stage.cu, transport.cu, group.cu). There is deliberately no CPU fallback:
 // every compute entry point fails loudly when no CUDA device is usable.
-#include "../../include/neutral_b200.h"
-
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <string>
 #include <vector>
 
-#include "transport.cuh"
+#include "engine.cuh"
 #include "nb_sincos.cuh"
+
+namespace nb {
+
+// microbench.cu
+int launch_red_rate(double* scratch, size_t cells, int nx, int iters, int pattern,
+                    cudaEvent_t e0, cudaEvent_t e1, double* seconds, double* reductions,
+                    cudaStream_t st);
+
+const OptionSpec kOptionSpecs[] = {
+    {"print", &Options::print, 0, 1},
+    {"pipeline", &Options::pipeline, 0, 1},
+    {"fast_div", &Options::fast_div, 0, 1},
+    {"tile_shift", &Options::tile_shift, -1, 12},
+    {"length_bins", &Options::length_bins, 0, 4096},
+    {"tally_prereduce", &Options::tally_prereduce, 0, 1},
+    {"l2_persist", &Options::l2_persist, 0, 2},
+    {"defer_finish", &Options::defer_finish, 0, 1},
+    {"device_inject", &Options::device_inject, 0, 1},
+    {"stage_overlap", &Options::stage_overlap, 0, 1},
+    {"history_smem_pad", &Options::history_smem_pad, 0, 200 * 1024},
+    {"ngpus", &Options::ngpus, 0, kMaxRanks},
+    {"collective", &Options::collective, 0, 1},
+    {"reduce_ctas", &Options::reduce_ctas, 1, 8192},
+    {"host_mirror", &Options::host_mirror, 0, 1},
+    {"headroom_pct", &Options::headroom_pct, 0, 1000},
+};
+const int kNumOptionSpecs = (int)(sizeof(kOptionSpecs) / sizeof(kOptionSpecs[0]));
+
+}  // namespace nb
 
 namespace {
 
@@ -31,118 +61,23 @@ const LogTable kHostLogTable = {
 #include "glibc_log_table.inc"
 };
 
-constexpr uint64_t kBankMagic = 0x6e62323030424e4bull;  // "nb200BNK"
+Options g_opt;                         // process-wide defaults
+bool g_env_read = false;
+DeviceCtx* g_ctx[kMaxDevices] = {nullptr};
+std::string g_last_error;
+Bank* g_last_deferred = nullptr;       // the bank nb200_solve_finish() refers to
+TallyGroup* g_mp = nullptr;            // multi-process group of this process (one GPU)
+std::vector<TallyGroup*> g_groups;     // every live group (tally-access hooks walk it)
+uint64_t g_replica_generation = 1;     // bumped by nb200_update_replicas
+int g_shard_first = 0, g_shard_count = -1;  // nb200_set_shard
 
-struct Bank {
-  BankView cur{};
-  BankView alt{};  // double buffer of the per-step sort (allocated on first use)
-  bool has_alt = false;
-  unsigned* keys = nullptr;
-  int n = 0;
-  int n_upper = 0;  // slots [n_upper, n) are known to hold dead particles
-  uint64_t pid0 = 0;
-  SoaView exported{};  // lazily allocated plain SoA view (11 arrays)
-  bool has_export = false;
+// What `validate` reports besides the reference's printed lines.
+struct StepLog {
+  uint64_t master_key, facets, collisions, processed, census, deaths, history_ns, sort_ns;
+  int ngpus;
 };
-
-// What inject_particles / nb200_bank_create hand out as `Particle*`: the reference's SoA
-// struct first (so -DSoA code can read the 11 pointers), our bookkeeping after it.
-struct BankHandle {
-  nb200_particle_soa view;
-  uint64_t magic;
-  Bank* impl;
-};
-
-constexpr int kCsBuckets = 8192;
-
-// Parameters of the bucket index of one table (CsStage in nb_bank.cuh).
-struct CsParams {
-  unsigned long long bits0 = 0;
-  int shift = 63;
-  int nb = 1;  // one bucket = plain bisection over the whole grid (always valid)
-};
-
-CsParams cs_params_from_host(const double* keys, int n) {
-  CsParams p;
-  if (n >= 2 && keys[0] > 0.0 && keys[n - 1] > keys[0]) {
-    unsigned long long lo, hi;
-    memcpy(&lo, &keys[0], 8);
-    memcpy(&hi, &keys[n - 1], 8);
-    p.bits0 = lo;
-    p.nb = kCsBuckets;
-    p.shift = 0;
-    while (((hi - lo) >> p.shift) >= (unsigned long long)p.nb) p.shift++;
-  }
-  return p;
-}
-
-struct Context {
-  bool ready = false;
-  int device = 0;
-  cudaStream_t stream = 0;
-  LogTable* d_logt = nullptr;
-  SinCosTable* d_sct = nullptr;
-  int opt_device_inject = 1;
-  unsigned long long* d_totals = nullptr;
-  unsigned long long* h_totals = nullptr;  // pinned, mapped
-  unsigned long long* h_totals_dev = nullptr;  // the same memory as the device addresses it
-  cudaEvent_t ev_begin = nullptr, ev_mid = nullptr, ev_end = nullptr;  // phase timing
-  // The density tile maps are only read by the event loop: they are staged on a side stream
-  // beside the begin-step / sort kernels (fork after the previous history kernel, join
-  // before the next one).
-  cudaStream_t stage_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_tiles = nullptr;
-  int opt_stage_overlap = 1;
-  int opt_history_smem_pad = 0;  // occupancy probe: extra dynamic shared memory per CTA
-  unsigned* d_bins = nullptr;  // histogram + cursors of the per-step sort
-  unsigned* d_n_live = nullptr;
-  int bins_capacity = 0;
-  int opt_fast_div = 1;
-  int opt_tile_shift = 8;
-  int opt_length_bins = 512;
-  int opt_tally_prereduce = 0;
-  int opt_l2_persist = 0;
-  int opt_defer_finish = 0;
-  Bank* pending_bank = nullptr;  // a step enqueued by solve_transport_2d, not yet finished
-  uint64_t pending_launches0 = 0;
-  bool l2_limit_set = false;
-  size_t l2_setaside = 0;
-  // mesh extent, read once per (edgex, edgey) pair for the sort's history-length estimate
-  const double* mesh_ex = nullptr;
-  const double* mesh_ey = nullptr;
-  double mesh_width = 1.0, mesh_height = 1.0;
-  struct MeshExtent {
-    const double* ex;
-    const double* ey;
-    int nx, ny;
-    double width, height;
-  };
-  std::vector<MeshExtent> mesh_cache;  // the last few (edgex, edgey) pairs seen
-  uint64_t launches = 0;
-  uint64_t last_stats[8] = {0};
-  int opt_print = 1;
-  int opt_pipeline = 1;
-  int shard_first = 0;
-  int shard_count = -1;
-  // cross-section grids seen last: same-grid detection and the bucket-index parameters are
-  // derived from a host copy of the keys once per (pointer, size) pair; the staging kernels
-  // re-verify them on the device every step (kTotFault)
-  const double* cs_s_keys = nullptr;
-  const double* cs_a_keys = nullptr;
-  int cs_n = 0, cs_a_n = 0;
-  int cs_same = 0;
-  CsParams cs_s_par, cs_a_par;
-  // per-step staging (stage.cu): cross-section tables and the density tile map
-  char* d_cs_stage = nullptr;
-  size_t cs_stage_bytes = 0;
-  double* d_tile_rho = nullptr;
-  int tile_capacity = 0;
-  double* d_edges4 = nullptr;
-  int edges_capacity = 0;
-  std::string last_error;
-};
-
-Context g;
+std::vector<StepLog> g_step_log;
+uint64_t g_last_stats[8] = {0};
 
 void set_error(const char* fmt, ...) {
   char buf[1024];
@@ -150,7 +85,7 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(buf, sizeof(buf), fmt, ap);
   va_end(ap);
-  g.last_error = buf;
+  g_last_error = buf;
 }
 
 [[noreturn]] void terminate(const char* fmt, ...) {
@@ -182,56 +117,157 @@ void set_error(const char* fmt, ...) {
     }                                                                               \
   } while (0)
 
-// Returns 0 when a device is usable and the context is initialised.
-int ensure_ready() {
-  if (g.ready) return 0;
+#define NCCL_FATAL(api, call)                                                          \
+  do {                                                                                 \
+    int rc__ = (call);                                                                 \
+    if (rc__ != kNcclSuccess)                                                          \
+      terminate("%s failed: %s [%s:%d]", #call, (api)->GetErrorString(rc__), __FILE__, \
+                __LINE__);                                                             \
+  } while (0)
+
+// Makes `dev` the current device for a scope.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+      CU_FATAL(cudaSetDevice(dev));
+      switched = true;
+    }
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+void read_environment() {
+  if (g_env_read) return;
+  g_env_read = true;
+  // NB200_NGPUS: GPUs the drop-in binary shards its bank over (SURVEY.md 5 "config / flags").
+  if (const char* s = getenv("NB200_NGPUS")) {
+    int count = 0;
+    if (strcmp(s, "all") == 0) {
+      if (cudaGetDeviceCount(&count) != cudaSuccess) count = 0;
+    } else {
+      count = atoi(s);
+    }
+    g_opt.ngpus = std::max(0, std::min(count, kMaxRanks));
+  }
+  if (const char* s = getenv("NB200_COLLECTIVE")) g_opt.collective = strcmp(s, "nccl") == 0 ? 0 : 1;
+  if (const char* s = getenv("NB200_HOST_MIRROR")) g_opt.host_mirror = atoi(s) != 0;
+  if (const char* s = getenv("NB200_HEADROOM_PCT")) g_opt.headroom_pct = std::max(0, atoi(s));
+}
+
+// The context of CUDA device `dev`, initialised on first use (`dev` must be current).
+// Returns nullptr with the error set.
+DeviceCtx* ctx_create(int dev) {
+  DeviceCtx* c = new DeviceCtx();
+  c->device = dev;
+#define CTX_TRY(call)                                                                    \
+  do {                                                                                   \
+    cudaError_t err__ = (call);                                                          \
+    if (err__ != cudaSuccess) {                                                          \
+      set_error("%s failed: %s [%s:%d]", #call, cudaGetErrorString(err__), __FILE__,     \
+                __LINE__);                                                               \
+      delete c;                                                                          \
+      return nullptr;                                                                    \
+    }                                                                                    \
+  } while (0)
+  CTX_TRY(cudaMalloc(&c->d_logt, sizeof(LogTable)));
+  CTX_TRY(cudaMemcpy(c->d_logt, &kHostLogTable, sizeof(LogTable), cudaMemcpyHostToDevice));
+  CTX_TRY(cudaMalloc(&c->d_sct, sizeof(SinCosTable)));
+  CTX_TRY(cudaMemcpy(c->d_sct, &kHostSinCosTable, sizeof(SinCosTable), cudaMemcpyHostToDevice));
+  CTX_TRY(cudaMalloc(&c->d_totals, sizeof(unsigned long long) * kTotCount));
+  CTX_TRY(cudaHostAlloc(&c->h_totals, sizeof(unsigned long long) * kTotCount * kRing,
+                        cudaHostAllocMapped | cudaHostAllocPortable));
+  memset(c->h_totals, 0, sizeof(unsigned long long) * kTotCount * kRing);
+  CTX_TRY(cudaHostGetDevicePointer(&c->h_totals_dev, c->h_totals, 0));
+  for (int k = 0; k < kRing; ++k) {
+    CTX_TRY(cudaEventCreate(&c->ev_begin[k]));
+    CTX_TRY(cudaEventCreate(&c->ev_mid[k]));
+    CTX_TRY(cudaEventCreate(&c->ev_end[k]));
+    CTX_TRY(cudaEventCreateWithFlags(&c->ev_pub[k], cudaEventDisableTiming));
+  }
+  CTX_TRY(cudaStreamCreateWithFlags(&c->stage_stream, cudaStreamNonBlocking));
+  CTX_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CTX_TRY(cudaEventCreateWithFlags(&c->ev_tiles, cudaEventDisableTiming));
+  CTX_TRY(cudaMalloc(&c->d_n_live, sizeof(unsigned)));
+#undef CTX_TRY
+  return c;
+}
+
+// Context of the CURRENT device; nullptr (error set) when no device is usable.
+DeviceCtx* ctx_current() {
+  read_environment();
   int count = 0;
   cudaError_t err = cudaGetDeviceCount(&count);
   if (err != cudaSuccess || count <= 0) {
     set_error("no CUDA device available (%s): the b200 kernel set has no CPU fallback",
               err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0");
     (void)cudaGetLastError();
-    return -1;
+    return nullptr;
   }
-  CU_TRY(cudaGetDevice(&g.device));
-  CU_TRY(cudaMalloc(&g.d_logt, sizeof(LogTable)));
-  CU_TRY(cudaMemcpy(g.d_logt, &kHostLogTable, sizeof(LogTable), cudaMemcpyHostToDevice));
-  CU_TRY(cudaMalloc(&g.d_sct, sizeof(SinCosTable)));
-  CU_TRY(cudaMemcpy(g.d_sct, &kHostSinCosTable, sizeof(SinCosTable), cudaMemcpyHostToDevice));
-  CU_TRY(cudaMalloc(&g.d_totals, sizeof(unsigned long long) * kTotCount));
-  CU_TRY(cudaHostAlloc(&g.h_totals, sizeof(unsigned long long) * kTotCount, cudaHostAllocMapped));
-  CU_TRY(cudaHostGetDevicePointer(&g.h_totals_dev, g.h_totals, 0));
-  CU_TRY(cudaEventCreate(&g.ev_begin));
-  CU_TRY(cudaEventCreate(&g.ev_mid));
-  CU_TRY(cudaEventCreate(&g.ev_end));
-  CU_TRY(cudaStreamCreateWithFlags(&g.stage_stream, cudaStreamNonBlocking));
-  CU_TRY(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
-  CU_TRY(cudaEventCreateWithFlags(&g.ev_tiles, cudaEventDisableTiming));
-  CU_TRY(cudaMalloc(&g.d_n_live, sizeof(unsigned)));
-  g.ready = true;
-  return 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+    set_error("cudaGetDevice failed");
+    return nullptr;
+  }
+  if (!g_ctx[dev]) g_ctx[dev] = ctx_create(dev);
+  return g_ctx[dev];
 }
 
-void require_ready() {
-  if (ensure_ready() != 0) terminate("%s", g.last_error.c_str());
+DeviceCtx& ctx_required() {
+  DeviceCtx* c = ctx_current();
+  if (!c) terminate("%s", g_last_error.c_str());
+  return *c;
 }
 
+// Context of device `dev` (made current for the call when it has to be created).
+DeviceCtx& ctx_on(int dev) {
+  if (dev < 0 || dev >= kMaxDevices) terminate("bad device ordinal %d", dev);
+  if (!g_ctx[dev]) {
+    DeviceGuard guard(dev);
+    g_ctx[dev] = ctx_create(dev);
+    if (!g_ctx[dev]) terminate("%s", g_last_error.c_str());
+  }
+  return *g_ctx[dev];
+}
+
+#define CTX_OR_RETURN(c)            \
+  DeviceCtx* c##_ptr = ctx_current(); \
+  if (!c##_ptr) return -1;           \
+  DeviceCtx& c = *c##_ptr
+
+// ------------------------------------------------------------------------------ options --
+int option_index(const char* name) {
+  for (int i = 0; i < kNumOptionSpecs; ++i)
+    if (strcmp(kOptionSpecs[i].name, name) == 0) return i;
+  return -1;
+}
+
+int opt_of(const Bank* bank, int Options::*slot) {
+  if (bank)
+    for (const auto& o : bank->overrides)
+      if (kOptionSpecs[o.first].slot == slot) return o.second;
+  return g_opt.*slot;
+}
+
+// --------------------------------------------------------------------------- allocation --
 template <typename T>
-size_t device_zalloc(T** buf, size_t len) {
-  require_ready();
+size_t device_zalloc(DeviceCtx& c, T** buf, size_t len) {
   const size_t bytes = sizeof(T) * (len ? len : 1);
   CU_FATAL(cudaMalloc((void**)buf, bytes));
-  CU_FATAL(cudaMemsetAsync(*buf, 0, bytes, g.stream));
+  CU_FATAL(cudaMemsetAsync(*buf, 0, bytes, c.stream));
   return sizeof(T) * len;
 }
 
-size_t bank_alloc(BankView& b, int n) {
+size_t bank_alloc(DeviceCtx& c, BankView& b, int n) {
   size_t bytes = 0;
-  bytes += device_zalloc(&b.pos, (size_t)n);
-  bytes += device_zalloc(&b.dir, (size_t)n);
-  bytes += device_zalloc(&b.ew, (size_t)n);
-  bytes += device_zalloc(&b.tm, (size_t)n);
-  bytes += device_zalloc(&b.meta, (size_t)n);
+  bytes += device_zalloc(c, &b.pos, (size_t)n);
+  bytes += device_zalloc(c, &b.dir, (size_t)n);
+  bytes += device_zalloc(c, &b.ew, (size_t)n);
+  bytes += device_zalloc(c, &b.tm, (size_t)n);
+  bytes += device_zalloc(c, &b.meta, (size_t)n);
   return bytes;
 }
 
@@ -244,13 +280,13 @@ void bank_release(BankView& b) {
   b = BankView{};
 }
 
-size_t soa_alloc(SoaView& s, int n) {
+size_t soa_alloc(DeviceCtx& c, SoaView& s, int n) {
   size_t bytes = 0;
   double** d[] = {&s.x, &s.y, &s.omega_x, &s.omega_y, &s.energy, &s.weight,
                   &s.dt_to_census, &s.mfp_to_collision};
-  for (double** p : d) bytes += device_zalloc(p, (size_t)n);
+  for (double** p : d) bytes += device_zalloc(c, p, (size_t)n);
   int** i[] = {&s.cellx, &s.celly, &s.dead};
-  for (int** p : i) bytes += device_zalloc(p, (size_t)n);
+  for (int** p : i) bytes += device_zalloc(c, p, (size_t)n);
   return bytes;
 }
 
@@ -279,321 +315,852 @@ nb200_particle_soa as_public(const SoaView& s) {
   return p;
 }
 
-BankHandle* new_handle(int n, uint64_t pid0, size_t* bytes) {
-  BankHandle* h = (BankHandle*)calloc(1, sizeof(BankHandle));
-  h->impl = new Bank();
+// Element offset view of a host SoA (the slice that one shard covers).
+SoaView soa_offset(const SoaView& s, size_t off) {
+  SoaView o;
+  o.x = s.x + off; o.y = s.y + off; o.omega_x = s.omega_x + off; o.omega_y = s.omega_y + off;
+  o.energy = s.energy + off; o.weight = s.weight + off;
+  o.dt_to_census = s.dt_to_census + off; o.mfp_to_collision = s.mfp_to_collision + off;
+  o.cellx = s.cellx + off; o.celly = s.celly + off; o.dead = s.dead + off;
+  return o;
+}
+
+nb200_particle_soa* views_of(BankHeader* h) { return reinterpret_cast<nb200_particle_soa*>(h + 1); }
+
+void set_views(Bank* bank, const nb200_particle_soa& v) {
+  nb200_particle_soa* views = views_of(bank->header);
+  for (uint64_t i = 0; i < bank->header->nviews; ++i) views[i] = v;
+}
+
+// omp3's thread split (omp3/neutral.c:64-74) applied to GPUs: shard g of G.
+void shard_split(int n, int g, int G, int* first, int* count) {
+  const int per = n / G, rem = n % G;
+  *first = g * per + std::min(g, rem);
+  *count = per + (g < rem ? 1 : 0);
+}
+
+// A new bank of n particles holding global particles [pid0, pid0 + n), sharded over `ngpus`
+// GPUs starting with the current one. Allocates the device arrays; fills nothing.
+Bank* new_bank(int n, uint64_t pid0, int ngpus, int headroom_pct, bool mirror, size_t* bytes) {
+  DeviceCtx& primary = ctx_required();
+  int count = 1;
+  CU_FATAL(cudaGetDeviceCount(&count));
+  ngpus = std::max(1, ngpus);
+  if (ngpus > count)
+    terminate("ngpus=%d GPUs requested (NB200_NGPUS / option ngpus) but only %d visible", ngpus,
+              count);
+  if (ngpus > 1 && g_mp)
+    terminate("a multi-process group is active on this process: banks are single-GPU");
+  Bank* bank = new Bank();
+  bank->n = n;
+  bank->pid0 = pid0;
+  bank->primary_dev = primary.device;
+  size_t total = 0;
+  for (int g = 0; g < ngpus; ++g) {
+    Shard sh;
+    sh.dev = (primary.device + g) % count;
+    shard_split(n, g, ngpus, &sh.first, &sh.n);
+    sh.pid0 = pid0 + (uint64_t)sh.first;
+    sh.n_upper = sh.n;
+    sh.capacity = sh.n + (int)(((long long)sh.n * headroom_pct + 99) / 100);
+    DeviceGuard guard(sh.dev);
+    total += bank_alloc(ctx_on(sh.dev), sh.cur, sh.capacity);
+    bank->shards.push_back(sh);
+  }
+  const uint64_t nviews = mirror ? (uint64_t)std::max(n, 1) : 1;
+  BankHeader* h = (BankHeader*)calloc(1, sizeof(BankHeader) + sizeof(nb200_particle_soa) * nviews);
+  if (!h) terminate("out of host memory for a bank handle of %llu views", (unsigned long long)nviews);
   h->magic = kBankMagic;
-  h->impl->n = n;
-  h->impl->n_upper = n;
-  h->impl->pid0 = pid0;
-  const size_t b = bank_alloc(h->impl->cur, n);
-  if (bytes) *bytes = b;
-  return h;
+  h->impl = bank;
+  h->nviews = nviews;
+  bank->header = h;
+  if (mirror) {
+    const size_t m = (size_t)std::max(n, 1);
+    nb200_particle_soa& a = bank->mirror.a;
+    double** d[] = {&a.x, &a.y, &a.omega_x, &a.omega_y, &a.energy, &a.weight, &a.dt_to_census,
+                    &a.mfp_to_collision};
+    for (double** p : d) CU_FATAL(cudaHostAlloc((void**)p, sizeof(double) * m, cudaHostAllocPortable));
+    int** i[] = {&a.cellx, &a.celly, &a.dead};
+    for (int** p : i) CU_FATAL(cudaHostAlloc((void**)p, sizeof(int) * m, cudaHostAllocPortable));
+    bank->mirror.present = true;
+    set_views(bank, a);
+  }
+  if (bytes) *bytes = total;
+  return bank;
 }
 
 Bank* bank_of(nb200_particle_soa* particles) {
   if (!particles) return nullptr;
-  BankHandle* h = reinterpret_cast<BankHandle*>(particles);
+  BankHeader* h = reinterpret_cast<BankHeader*>(particles) - 1;
   if (h->magic != kBankMagic || !h->impl) return nullptr;
   return h->impl;
 }
 
-// Uploads a host SoA bank (count slots) into device bank b, tagging origins from 0.
-void upload_host_soa(const SoaView& host, int count, BankView& dst) {
-  SoaView staging{};
-  soa_alloc(staging, count);
-  const double* hd[] = {host.x, host.y, host.omega_x, host.omega_y, host.energy, host.weight,
-                        host.dt_to_census, host.mfp_to_collision};
-  double* dd[] = {staging.x, staging.y, staging.omega_x, staging.omega_y, staging.energy,
-                  staging.weight, staging.dt_to_census, staging.mfp_to_collision};
-  for (int k = 0; k < 8; ++k)
-    CU_FATAL(cudaMemcpyAsync(dd[k], hd[k], sizeof(double) * count, cudaMemcpyHostToDevice,
-                             g.stream));
-  const int* hi[] = {host.cellx, host.celly, host.dead};
-  int* di[] = {staging.cellx, staging.celly, staging.dead};
-  for (int k = 0; k < 3; ++k)
-    CU_FATAL(cudaMemcpyAsync(di[k], hi[k], sizeof(int) * count, cudaMemcpyHostToDevice,
-                             g.stream));
-  g.launches += launch_import_soa(dst, staging, count, 0, g.stream);
-  CU_FATAL(cudaStreamSynchronize(g.stream));
-  soa_release(staging);
+nb200_particle_soa* handle_of(Bank* bank) { return views_of(bank->header); }
+
+bool single_shard(const Bank* bank) { return bank->shards.size() == 1; }
+
+// Uploads host SoA slices into the shards of `bank` (origins from 0 within each shard).
+void upload_host_soa(Bank* bank, const SoaView& host) {
+  for (Shard& sh : bank->shards) {
+    if (sh.n <= 0) continue;
+    DeviceGuard guard(sh.dev);
+    DeviceCtx& c = ctx_on(sh.dev);
+    SoaView staging{};
+    soa_alloc(c, staging, sh.n);
+    const SoaView h = soa_offset(host, (size_t)sh.first);
+    const double* hd[] = {h.x, h.y, h.omega_x, h.omega_y, h.energy, h.weight, h.dt_to_census,
+                          h.mfp_to_collision};
+    double* dd[] = {staging.x, staging.y, staging.omega_x, staging.omega_y, staging.energy,
+                    staging.weight, staging.dt_to_census, staging.mfp_to_collision};
+    for (int k = 0; k < 8; ++k)
+      CU_FATAL(cudaMemcpyAsync(dd[k], hd[k], sizeof(double) * sh.n, cudaMemcpyHostToDevice,
+                               c.stream));
+    const int* hi[] = {h.cellx, h.celly, h.dead};
+    int* di[] = {staging.cellx, staging.celly, staging.dead};
+    for (int k = 0; k < 3; ++k)
+      CU_FATAL(cudaMemcpyAsync(di[k], hi[k], sizeof(int) * sh.n, cudaMemcpyHostToDevice,
+                               c.stream));
+    c.launches += launch_import_soa(sh.cur, staging, sh.n, 0, c.stream);
+    CU_FATAL(cudaStreamSynchronize(c.stream));
+    soa_release(staging);
+    sh.n_upper = sh.n;
+  }
 }
 
-// Looks at the two energy grids once per (pointer, size) pair: are they the same grid, and
-// which leading bits spread their keys over the bucket index.
-// A host that alternates between a few working sets (bench.py's double-buffered e2e pipeline)
-// shows a few pairs in turn: the last kTableCacheSlots are remembered, so that no timestep of
-// a known pair issues a device-to-host copy - which would queue behind whatever bulk download
-// the host has in flight on the same copy engine.
-struct InspectedTables {
-  const double* s_keys;
-  const double* a_keys;
-  int s_n, a_n, same;
-  CsParams s_par, a_par;
-};
-constexpr size_t kTableCacheSlots = 8;
-std::vector<InspectedTables> g_table_cache;
+void ensure_export(DeviceCtx& c, Shard& sh) {
+  if (sh.has_export) return;
+  soa_alloc(c, sh.exported, sh.capacity);
+  sh.has_export = true;
+}
 
-int inspect_tables(const double* s_keys, int s_n, const double* a_keys, int a_n) {
-  if (g.cs_s_keys == s_keys && g.cs_a_keys == a_keys && g.cs_n == s_n && g.cs_a_n == a_n)
-    return g.cs_same;
-  for (const InspectedTables& t : g_table_cache) {
-    if (t.s_keys == s_keys && t.a_keys == a_keys && t.s_n == s_n && t.a_n == a_n) {
-      g.cs_s_keys = s_keys;
-      g.cs_a_keys = a_keys;
-      g.cs_n = s_n;
-      g.cs_a_n = a_n;
-      g.cs_same = t.same;
-      g.cs_s_par = t.s_par;
-      g.cs_a_par = t.a_par;
-      return g.cs_same;
-    }
+// Copies the bank to host SoA arrays in injection order (synchronous).
+void download_to_host(Bank* bank, const SoaView& host) {
+  for (Shard& sh : bank->shards) {
+    if (sh.n <= 0) continue;
+    DeviceGuard guard(sh.dev);
+    DeviceCtx& c = ctx_on(sh.dev);
+    ensure_export(c, sh);
+    c.launches += launch_export_soa(sh.cur, sh.exported, sh.n, c.stream);
+    const SoaView& s = sh.exported;
+    const SoaView h = soa_offset(host, (size_t)sh.first);
+    const double* dd[] = {s.x, s.y, s.omega_x, s.omega_y, s.energy, s.weight, s.dt_to_census,
+                          s.mfp_to_collision};
+    double* hd[] = {h.x, h.y, h.omega_x, h.omega_y, h.energy, h.weight, h.dt_to_census,
+                    h.mfp_to_collision};
+    for (int k = 0; k < 8; ++k)
+      CU_FATAL(cudaMemcpyAsync(hd[k], dd[k], sizeof(double) * sh.n, cudaMemcpyDeviceToHost,
+                               c.stream));
+    const int* di[] = {s.cellx, s.celly, s.dead};
+    int* hi[] = {h.cellx, h.celly, h.dead};
+    for (int k = 0; k < 3; ++k)
+      CU_FATAL(cudaMemcpyAsync(hi[k], di[k], sizeof(int) * sh.n, cudaMemcpyDeviceToHost,
+                               c.stream));
   }
-  std::vector<double> hs(std::max(s_n, 1)), ha(std::max(a_n, 1));
-  CU_FATAL(cudaMemcpyAsync(hs.data(), s_keys, sizeof(double) * s_n, cudaMemcpyDeviceToHost,
-                           g.stream));
-  CU_FATAL(cudaMemcpyAsync(ha.data(), a_keys, sizeof(double) * a_n, cudaMemcpyDeviceToHost,
-                           g.stream));
-  CU_FATAL(cudaStreamSynchronize(g.stream));
-  g.cs_s_keys = s_keys;
-  g.cs_a_keys = a_keys;
-  g.cs_n = s_n;
-  g.cs_a_n = a_n;
-  g.cs_same = s_n == a_n && memcmp(hs.data(), ha.data(), sizeof(double) * s_n) == 0;
-  g.cs_s_par = cs_params_from_host(hs.data(), s_n);
-  g.cs_a_par = cs_params_from_host(ha.data(), a_n);
-  if (g_table_cache.size() >= kTableCacheSlots) g_table_cache.erase(g_table_cache.begin());
-  g_table_cache.push_back({s_keys, a_keys, s_n, a_n, g.cs_same, g.cs_s_par, g.cs_a_par});
-  return g.cs_same;
+  for (Shard& sh : bank->shards) {
+    DeviceGuard guard(sh.dev);
+    CU_FATAL(cudaStreamSynchronize(ctx_on(sh.dev).stream));
+  }
+}
+
+void refresh_mirror(Bank* bank) {
+  if (bank->mirror.present) download_to_host(bank, as_soa_view(bank->mirror.a));
+}
+
+// --------------------------------------------------------------------- scheduling hints --
+CsParams cs_params_from_ends(double k_first, double k_last, int n) {
+  CsParams p;
+  if (n >= 2 && k_first > 0.0 && k_last > k_first) {
+    unsigned long long lo, hi;
+    memcpy(&lo, &k_first, 8);
+    memcpy(&hi, &k_last, 8);
+    p.bits0 = lo;
+    p.nb = kCsBuckets;
+    p.shift = 0;
+    while (((hi - lo) >> p.shift) >= (unsigned long long)p.nb) p.shift++;
+  }
+  return p;
+}
+
+// Which leading bits spread a table's keys over its bucket index: read off the first and the
+// last key once per (pointer, size). A hint, not an input: the index is exact for any
+// parameters (nb_bank.cuh: CsStage), stale ones only fill the buckets less evenly. Cached so
+// that no timestep of a known table issues a device-to-host copy, which would queue behind
+// whatever bulk download the caller has in flight on the same copy engine.
+CsParams table_hint(DeviceCtx& c, const double* keys, int n) {
+  for (const auto& t : c.table_cache)
+    if (t.keys == keys && t.n == n) return t.par;
+  double ends[2] = {0.0, 0.0};
+  if (n >= 2) {
+    CU_FATAL(cudaMemcpyAsync(&ends[0], keys, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    CU_FATAL(cudaMemcpyAsync(&ends[1], keys + n - 1, sizeof(double), cudaMemcpyDeviceToHost,
+                             c.stream));
+    CU_FATAL(cudaStreamSynchronize(c.stream));
+  }
+  const CsParams par = cs_params_from_ends(ends[0], ends[1], n);
+  if (c.table_cache.size() >= 16) c.table_cache.erase(c.table_cache.begin());
+  c.table_cache.push_back({keys, n, par});
+  return par;
+}
+
+// Extent of the mesh, for the sort's history-length estimate (a scheduling hint only).
+void mesh_hint(DeviceCtx& c, const double* edgex, const double* edgey, int nx, int ny,
+               double* width, double* height) {
+  for (const auto& m : c.mesh_cache)
+    if (m.ex == edgex && m.ey == edgey && m.nx == nx && m.ny == ny) {
+      *width = m.width;
+      *height = m.height;
+      return;
+    }
+  double ex[2], ey[2];
+  CU_FATAL(cudaMemcpyAsync(&ex[0], edgex, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  CU_FATAL(cudaMemcpyAsync(&ex[1], edgex + nx, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  CU_FATAL(cudaMemcpyAsync(&ey[0], edgey, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  CU_FATAL(cudaMemcpyAsync(&ey[1], edgey + ny, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  CU_FATAL(cudaStreamSynchronize(c.stream));
+  *width = ex[1] > ex[0] ? ex[1] - ex[0] : 1.0;
+  *height = ey[1] > ey[0] ? ey[1] - ey[0] : 1.0;
+  if (c.mesh_cache.size() >= 16) c.mesh_cache.erase(c.mesh_cache.begin());
+  c.mesh_cache.push_back({edgex, edgey, nx, ny, *width, *height});
 }
 
 // The step totals reach the host through mapped pinned memory, written by the device itself:
 // a cudaMemcpyAsync would wait its turn on the device-to-host copy engine behind any bulk
 // download the caller has in flight (measured: 3.4 ms per deck run in bench.py's e2e loop).
+// In a sharded run the same kernel raises the rank's `ready` flag: the history kernel in front
+// of it in stream order has deposited the whole delta (nb_group.cuh).
 __global__ void k_publish_totals(const unsigned long long* __restrict__ totals,
-                                 volatile unsigned long long* host_totals) {
-  if (threadIdx.x < kTotCount) host_totals[threadIdx.x] = totals[threadIdx.x];
+                                 volatile unsigned long long* host_totals, SyncBlock* sync,
+                                 unsigned long long epoch) {
+  if (threadIdx.x < kTotCount) {
+    unsigned long long v = totals[threadIdx.x];
+    if (sync && threadIdx.x == kTotGroupFault) v = sync->fault;
+    host_totals[threadIdx.x] = v;
+  }
   __threadfence_system();
+  if (sync && threadIdx.x == 0)
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&sync->ready), "l"(epoch) : "memory");
 }
 
-// Restages both tables into the library's own block (stage.cu) and fills the views.
-void stage_tables(StepArgs& a) {
+// Restages both tables into the device's own block (stage.cu) and fills the views.
+void stage_tables(DeviceCtx& c, StepArgs& a) {
+  const CsParams ps = table_hint(c, a.s_keys, a.s_n), pa = table_hint(c, a.a_keys, a.a_n);
   auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t kv_s = align(sizeof(double2) * a.s_n), kv_a = align(sizeof(double2) * a.a_n);
-  const size_t bk_s = align(sizeof(int) * (g.cs_s_par.nb + 1));
-  const size_t bk_a = align(sizeof(int) * (g.cs_a_par.nb + 1));
+  const size_t bk_s = align(sizeof(int) * (ps.nb + 1));
+  const size_t bk_a = align(sizeof(int) * (pa.nb + 1));
   const size_t need = kv_s + kv_a + bk_s + bk_a;
-  if (g.cs_stage_bytes < need) {
-    cudaFree(g.d_cs_stage);
-    CU_FATAL(cudaMalloc(&g.d_cs_stage, need));
-    g.cs_stage_bytes = need;
+  if (c.cs_stage_bytes < need) {
+    // the block may still be read by a timestep in flight: freeing synchronises the device
+    cudaFree(c.d_cs_stage);
+    CU_FATAL(cudaMalloc(&c.d_cs_stage, need));
+    c.cs_stage_bytes = need;
   }
-  char* p = g.d_cs_stage;
+  char* p = c.d_cs_stage;
   double2* d_kv_s = (double2*)p; p += kv_s;
   double2* d_kv_a = (double2*)p; p += kv_a;
   int* d_bk_s = (int*)p; p += bk_s;
   int* d_bk_a = (int*)p;
-  g.launches += launch_stage_cs(a.s_keys, a.s_vals, a.s_n, d_kv_s, d_bk_s, g.cs_s_par.bits0,
-                                g.cs_s_par.shift, g.cs_s_par.nb,
-                                a.same_keys ? a.a_keys : nullptr, a.totals, g.stream);
-  g.launches += launch_stage_cs(a.a_keys, a.a_vals, a.a_n, d_kv_a, d_bk_a, g.cs_a_par.bits0,
-                                g.cs_a_par.shift, g.cs_a_par.nb, nullptr, a.totals, g.stream);
-  a.cs_s = CsStage{d_kv_s, d_bk_s, g.cs_s_par.bits0, g.cs_s_par.shift, g.cs_s_par.nb, a.s_n};
-  a.cs_a = CsStage{d_kv_a, d_bk_a, g.cs_a_par.bits0, g.cs_a_par.shift, g.cs_a_par.nb, a.a_n};
+  c.launches += launch_stage_cs(a.s_keys, a.s_vals, a.s_n, d_kv_s, d_bk_s, ps.bits0, ps.shift,
+                                ps.nb, a.same_keys ? a.a_keys : nullptr, a.totals, c.stream);
+  c.launches += launch_stage_cs(a.a_keys, a.a_vals, a.a_n, d_kv_a, d_bk_a, pa.bits0, pa.shift,
+                                pa.nb, nullptr, a.totals, c.stream);
+  a.cs_s = CsStage{d_kv_s, d_bk_s, ps.bits0, ps.shift, ps.nb, a.s_n};
+  a.cs_a = CsStage{d_kv_a, d_bk_a, pa.bits0, pa.shift, pa.nb, a.a_n};
 }
 
-void stage_tiles(StepArgs& a, cudaStream_t st) {
+void stage_tiles(DeviceCtx& c, StepArgs& a, cudaStream_t st) {
   const int nfine = (((a.nx - 1) >> kTileShift) + 1) * (((a.ny - 1) >> kTileShift) + 1);
   const int ncoarse = (((a.nx - 1) >> kCoarseShift) + 1) * (((a.ny - 1) >> kCoarseShift) + 1);
-  if (g.tile_capacity < nfine + ncoarse) {
-    cudaFree(g.d_tile_rho);
-    CU_FATAL(cudaMalloc(&g.d_tile_rho, sizeof(double) * (nfine + ncoarse)));
-    g.tile_capacity = nfine + ncoarse;
+  if (c.tile_capacity < nfine + ncoarse) {
+    cudaFree(c.d_tile_rho);
+    CU_FATAL(cudaMalloc(&c.d_tile_rho, sizeof(double) * (nfine + ncoarse)));
+    c.tile_capacity = nfine + ncoarse;
   }
-  g.launches += launch_stage_tiles(a.density, a.nx, a.ny, g.d_tile_rho, g.d_tile_rho + nfine,
+  c.launches += launch_stage_tiles(a.density, a.nx, a.ny, c.d_tile_rho, c.d_tile_rho + nfine,
                                    &a.tiles, st);
   // ... and the target-edge rows (same consumer: the event loop only)
   const int stride = ((std::max(a.nx, a.ny) + 1 + 31) / 32) * 32;
-  if (g.edges_capacity < 4 * stride) {
-    cudaFree(g.d_edges4);
-    CU_FATAL(cudaMalloc(&g.d_edges4, sizeof(double) * 4 * (size_t)stride));
-    g.edges_capacity = 4 * stride;
+  if (c.edges_capacity < 4 * stride) {
+    cudaFree(c.d_edges4);
+    CU_FATAL(cudaMalloc(&c.d_edges4, sizeof(double) * 4 * (size_t)stride));
+    c.edges_capacity = 4 * stride;
   }
-  g.launches += launch_stage_edges(a.edgex, a.nx, a.edgey, a.ny, stride, g.d_edges4, st);
-  a.edges4 = g.d_edges4;
+  c.launches += launch_stage_edges(a.edgex, a.nx, a.edgey, a.ny, stride, c.d_edges4, st);
+  a.edges4 = c.d_edges4;
   a.edge_stride = stride;
 }
 
-void finish_step(uint64_t* facet_events, uint64_t* collision_events);
-
-// The one timestep both flavours share. All pointers are device memory.
-void run_step(Bank* bank, int nx, int ny, uint64_t master_key, double dt, int ntotal,
-              const double* density, const double* edgex, const double* edgey,
-              const double* s_keys, const double* s_vals, int s_n, const double* a_keys,
-              const double* a_vals, int a_n, double* tally, uint64_t* r0, uint64_t* r1,
-              uint64_t* r2, uint64_t* facet_events, uint64_t* collision_events) {
-  if (g.pending_bank)
-    terminate("solve_transport_2d: the previous timestep was enqueued with defer_finish=1 and "
-              "nb200_solve_finish has not been called");
-  const uint64_t launches0 = g.launches;
-  StepArgs a{};
-  a.nx = nx;
-  a.ny = ny;
-  a.n = bank->n;
-  a.master_key = master_key;
-  a.pid0 = bank->pid0;
-  a.dt = dt;
-  a.inv_ntotal = 1.0 / (double)ntotal;  // omp3/neutral.c:120
-  a.density = density;
-  a.edgex = edgex;
-  a.edgey = edgey;
-  a.s_keys = s_keys;
-  a.s_vals = s_vals;
-  a.s_n = s_n;
-  a.a_keys = a_keys;
-  a.a_vals = a_vals;
-  a.a_n = a_n;
-  a.same_keys = inspect_tables(s_keys, s_n, a_keys, a_n);
-  a.tally = tally;
-  a.p_facets = (unsigned long long*)r0;
-  a.p_collisions = (unsigned long long*)r1;
-  a.p_census = (unsigned long long*)r2;
-  a.totals = g.d_totals;
-  a.bank = bank->cur;
-  a.logt = g.d_logt;
-
-  CU_FATAL(cudaMemsetAsync(g.d_totals, 0, sizeof(unsigned long long) * kTotCount, g.stream));
-  CU_FATAL(cudaEventRecord(g.ev_begin, g.stream));
-  if (g.opt_pipeline) {
-    if (g.mesh_ex != edgex || g.mesh_ey != edgey) {  // extent of the mesh (a scheduling hint)
-      bool known = false;
-      for (const auto& m : g.mesh_cache)
-        if (m.ex == edgex && m.ey == edgey && m.nx == nx && m.ny == ny) {
-          g.mesh_width = m.width;
-          g.mesh_height = m.height;
-          known = true;
-        }
-      if (!known) {
-        double ex[2], ey[2];
-        CU_FATAL(cudaMemcpyAsync(&ex[0], edgex, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-        CU_FATAL(cudaMemcpyAsync(&ex[1], edgex + nx, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-        CU_FATAL(cudaMemcpyAsync(&ey[0], edgey, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-        CU_FATAL(cudaMemcpyAsync(&ey[1], edgey + ny, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-        CU_FATAL(cudaStreamSynchronize(g.stream));
-        g.mesh_width = ex[1] > ex[0] ? ex[1] - ex[0] : 1.0;
-        g.mesh_height = ey[1] > ey[0] ? ey[1] - ey[0] : 1.0;
-        if (g.mesh_cache.size() >= 8) g.mesh_cache.erase(g.mesh_cache.begin());
-        g.mesh_cache.push_back({edgex, edgey, nx, ny, g.mesh_width, g.mesh_height});
-      }
-      g.mesh_ex = edgex;
-      g.mesh_ey = edgey;
+int take_slot(DeviceCtx& c) {
+  for (int tries = 0; tries < kRing; ++tries) {
+    const int s = (c.next_slot + tries) % kRing;
+    if (!c.slot_busy[s]) {
+      c.slot_busy[s] = true;
+      c.next_slot = (s + 1) % kRing;
+      return s;
     }
-    if (g.opt_l2_persist && !g.l2_limit_set) {  // set-aside for the persisting window
+  }
+  terminate("more than %d timesteps in flight on GPU %d: collect them with nb200_solve_finish",
+            kRing, c.device);
+}
+
+// What one shard's timestep reads and writes, as pointers on the shard's own GPU.
+struct ShardIO {
+  const double *density, *edgex, *edgey, *s_keys, *s_vals, *a_keys, *a_vals;
+  double* tally;
+  uint64_t *r0, *r1, *r2;
+};
+
+// Enqueues one timestep of one shard on its device's stream (the device is current).
+void enqueue_shard_step(DeviceCtx& c, const Bank* bank, Shard& sh, const StepRequest& rq,
+                        const ShardIO& io, int slot, SyncBlock* sync, unsigned long long epoch) {
+  StepArgs a{};
+  a.nx = rq.nx;
+  a.ny = rq.ny;
+  a.n = sh.n;
+  a.master_key = rq.master_key;
+  a.pid0 = sh.pid0;
+  a.dt = rq.dt;
+  a.inv_ntotal = 1.0 / (double)rq.ntotal;  // omp3/neutral.c:120
+  a.density = io.density;
+  a.edgex = io.edgex;
+  a.edgey = io.edgey;
+  a.s_keys = io.s_keys;
+  a.s_vals = io.s_vals;
+  a.s_n = rq.s_n;
+  a.a_keys = io.a_keys;
+  a.a_vals = io.a_vals;
+  a.a_n = rq.a_n;
+  a.same_keys = rq.s_n == rq.a_n;  // necessary; the staging kernel decides (same_grid())
+  a.tally = io.tally;
+  a.p_facets = (unsigned long long*)io.r0;
+  a.p_collisions = (unsigned long long*)io.r1;
+  a.p_census = (unsigned long long*)io.r2;
+  a.totals = c.d_totals;
+  a.bank = sh.cur;
+  a.logt = c.d_logt;
+
+  const int opt_l2 = opt_of(bank, &Options::l2_persist);
+  CU_FATAL(cudaMemsetAsync(c.d_totals, 0, sizeof(unsigned long long) * kTotCount, c.stream));
+  CU_FATAL(cudaEventRecord(c.ev_begin[slot], c.stream));
+  if (opt_of(bank, &Options::pipeline)) {
+    double mesh_w = 1.0, mesh_h = 1.0;
+    mesh_hint(c, io.edgex, io.edgey, rq.nx, rq.ny, &mesh_w, &mesh_h);
+    if (opt_l2 && !c.l2_limit_set) {  // set-aside for the persisting window
       size_t want = 4u << 20;
-      if (g.opt_l2_persist == 2) {  // experiment: persist (part of) the tally instead
+      if (opt_l2 == 2) {  // experiment: persist (part of) the tally instead
         int max_bytes = 0;
-        CU_FATAL(cudaDeviceGetAttribute(&max_bytes, cudaDevAttrMaxPersistingL2CacheSize, g.device));
+        CU_FATAL(cudaDeviceGetAttribute(&max_bytes, cudaDevAttrMaxPersistingL2CacheSize, c.device));
         want = (size_t)max_bytes;
       }
       CU_FATAL(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
-      CU_FATAL(cudaDeviceGetLimit(&g.l2_setaside, cudaLimitPersistingL2CacheSize));
-      g.l2_limit_set = true;
+      CU_FATAL(cudaDeviceGetLimit(&c.l2_setaside, cudaLimitPersistingL2CacheSize));
+      c.l2_limit_set = true;
     }
     // P0: restage the read-only inputs (cross-section tables, density tile map)
-    const bool overlap = g.opt_stage_overlap != 0;
+    const bool overlap = opt_of(bank, &Options::stage_overlap) != 0;
     if (overlap) {
-      CU_FATAL(cudaEventRecord(g.ev_fork, g.stream));
-      CU_FATAL(cudaStreamWaitEvent(g.stage_stream, g.ev_fork, 0));
-      stage_tiles(a, g.stage_stream);
-      CU_FATAL(cudaEventRecord(g.ev_tiles, g.stage_stream));
+      CU_FATAL(cudaEventRecord(c.ev_fork, c.stream));
+      CU_FATAL(cudaStreamWaitEvent(c.stage_stream, c.ev_fork, 0));
+      stage_tiles(c, a, c.stage_stream);
+      CU_FATAL(cudaEventRecord(c.ev_tiles, c.stage_stream));
     }
-    stage_tables(a);
-    if (!overlap) stage_tiles(a, g.stream);
+    stage_tables(c, a);
+    if (!overlap) stage_tiles(c, a, c.stream);
     // P1-P3: begin-step set-up, classification and counting sort into the double buffer
     SortArgs s{};
-    s.tile_shift = g.opt_tile_shift;
-    s.tiles_x = s.tile_shift >= 0 ? ((nx - 1) >> s.tile_shift) + 1 : 1;
-    s.ntiles = s.tile_shift >= 0 ? s.tiles_x * (((ny - 1) >> s.tile_shift) + 1) : 1;
-    s.nq = g.opt_length_bins > 1 ? g.opt_length_bins : 1;
+    s.nq = std::max(opt_of(bank, &Options::length_bins), 1);
+    s.tile_shift = opt_of(bank, &Options::tile_shift);
+    // 3 classes x length bins x tiles + the dead bin, in 64 bits; a combination that asks for
+    // more bins than the scratch is worth gets coarser tiles (a scheduling key, nothing else)
+    long long ntiles = 1, tiles_x = 1;
+    for (;; ++s.tile_shift) {
+      tiles_x = s.tile_shift >= 0 ? ((rq.nx - 1) >> s.tile_shift) + 1 : 1;
+      ntiles = s.tile_shift >= 0 ? tiles_x * (((rq.ny - 1) >> s.tile_shift) + 1) : 1;
+      if (s.tile_shift < 0 || 3ll * s.nq * ntiles + 1 <= (1ll << 24)) break;
+    }
+    s.tiles_x = (int)tiles_x;
+    s.ntiles = (int)ntiles;
     s.q_scale = 24.0f;  // 12 bins across the sqrt(2) spread of facet counts with direction
-    s.inv_dx = (float)((double)nx / g.mesh_width);
-    s.inv_dy = (float)((double)ny / g.mesh_height);
+    s.inv_dx = (float)((double)rq.nx / mesh_w);
+    s.inv_dy = (float)((double)rq.ny / mesh_h);
     s.nbins = 3 * s.nq * s.ntiles + 1;
-    s.n_upper = bank->n_upper;
-    s.n = bank->n;
-    if (!bank->has_alt) {
-      bank_alloc(bank->alt, bank->n);
-      device_zalloc(&bank->keys, (size_t)bank->n);
-      bank->has_alt = true;
+    s.n_upper = sh.n_upper;
+    s.n = sh.n;
+    if (!sh.has_alt) {
+      bank_alloc(c, sh.alt, sh.capacity);
+      device_zalloc(c, &sh.keys, (size_t)sh.capacity);
+      sh.has_alt = true;
     }
-    if (g.bins_capacity < s.nbins) {
-      cudaFree(g.d_bins);
+    if (c.bins_capacity < s.nbins) {
+      cudaFree(c.d_bins);
       // histogram, cursors, and one scan partial per 2048 bins
-      CU_FATAL(cudaMalloc(&g.d_bins, sizeof(unsigned) * (2 * (size_t)s.nbins + s.nbins / 2048 + 1)));
-      g.bins_capacity = s.nbins;
+      CU_FATAL(cudaMalloc(&c.d_bins, sizeof(unsigned) * (2 * (size_t)s.nbins + s.nbins / 2048 + 1)));
+      c.bins_capacity = s.nbins;
     }
-    s.keys = bank->keys;
-    s.bin_count = g.d_bins;
-    s.bin_cursor = g.d_bins + s.nbins;
-    s.chunk_sum = g.d_bins + 2 * (size_t)s.nbins;
-    s.n_live = g.d_n_live;
-    g.launches += launch_sort_phase(a, s, bank->alt, g.stream);
-    std::swap(bank->cur, bank->alt);
-    a.bank = bank->cur;
-    if (overlap) CU_FATAL(cudaStreamWaitEvent(g.stream, g.ev_tiles, 0));
-    CU_FATAL(cudaEventRecord(g.ev_mid, g.stream));
+    s.keys = sh.keys;
+    s.bin_count = c.d_bins;
+    s.bin_cursor = c.d_bins + s.nbins;
+    s.chunk_sum = c.d_bins + 2 * (size_t)s.nbins;
+    s.n_live = c.d_n_live;
+    c.launches += launch_sort_phase(a, s, sh.alt, c.stream);
+    if (s.n_upper > 0) {  // the sort ran: the double buffer now holds the bank
+      std::swap(sh.cur, sh.alt);
+      a.bank = sh.cur;
+    }
+    if (overlap) CU_FATAL(cudaStreamWaitEvent(c.stream, c.ev_tiles, 0));
+    CU_FATAL(cudaEventRecord(c.ev_mid[slot], c.stream));
     // P4: event loop over the sorted live prefix
-    g.launches += launch_history(a, g.d_n_live, s.n_upper, g.opt_fast_div != 0,
-                                 g.opt_tally_prereduce != 0,
-                                 g.opt_l2_persist == 2 ? (const void*)tally
-                                 : g.opt_l2_persist   ? (const void*)g.d_cs_stage : nullptr,
-                                 g.opt_l2_persist == 2 ? sizeof(double) * (size_t)nx * ny
-                                                       : g.cs_stage_bytes,
-                                 g.opt_l2_persist == 2 ? g.l2_setaside : 0,
-                                 g.opt_history_smem_pad, g.stream);
+    const bool fast_div = opt_of(bank, &Options::fast_div) != 0;
+    c.launches += launch_history(a, c.d_n_live, s.n_upper, fast_div,
+                                 opt_of(bank, &Options::tally_prereduce) != 0,
+                                 opt_l2 == 2 ? (const void*)io.tally
+                                 : opt_l2    ? (const void*)c.d_cs_stage : nullptr,
+                                 opt_l2 == 2 ? sizeof(double) * (size_t)rq.nx * rq.ny
+                                             : c.cs_stage_bytes,
+                                 opt_l2 == 2 ? c.l2_setaside : 0,
+                                 opt_of(bank, &Options::history_smem_pad), c.stream);
   } else {
-    CU_FATAL(cudaEventRecord(g.ev_mid, g.stream));
-    g.launches += launch_history_direct(a, g.stream);
+    if (a.same_keys)
+      c.launches += launch_compare_grids(a.s_keys, a.a_keys, a.s_n, a.totals, c.stream);
+    CU_FATAL(cudaEventRecord(c.ev_mid[slot], c.stream));
+    c.launches += launch_history_direct(a, c.stream);
   }
   CU_FATAL(cudaGetLastError());
-  CU_FATAL(cudaEventRecord(g.ev_end, g.stream));
-  k_publish_totals<<<1, 32, 0, g.stream>>>(g.d_totals, g.h_totals_dev);
-  g.launches += 1;
-  g.pending_bank = bank;
-  g.pending_launches0 = launches0;
-  // "defer_finish": the caller overlaps its own host work (launching the collective that
-  // combines this step's tally delta, say) with the step and collects the counts later
-  if (!g.opt_defer_finish) finish_step(facet_events, collision_events);
+  CU_FATAL(cudaEventRecord(c.ev_end[slot], c.stream));
+  k_publish_totals<<<1, 32, 0, c.stream>>>(c.d_totals, c.h_totals_dev + (size_t)slot * kTotCount,
+                                           sync, epoch);
+  CU_FATAL(cudaEventRecord(c.ev_pub[slot], c.stream));
+  c.launches += 1;
+  c.pending_steps++;
 }
 
-// Second half of a timestep: waits for the stream, checks the device-side faults, updates
-// the live-prefix bound and hands the counts to the caller (omp3/neutral.c:202-205).
-void finish_step(uint64_t* facet_events, uint64_t* collision_events) {
-  Bank* bank = g.pending_bank;
-  if (!bank) return;
-  g.pending_bank = nullptr;
-  const uint64_t launches0 = g.pending_launches0;
-  CU_FATAL(cudaStreamSynchronize(g.stream));
-  if (g.h_totals[kTotFault])
-    terminate("solve_transport_2d: the cross-section tables are not what they were when first "
-              "seen (energy grid not strictly increasing, or the two grids no longer equal)");
-  // The sort compacted every particle that was dead at the start of this step behind the
-  // live prefix; particles that died DURING the step still sit inside the prefix (the next
-  // sort moves them out), so the prefix to visit next step is this step's live count.
-  if (g.opt_pipeline) bank->n_upper = (int)g.h_totals[kTotProcessed];
+// ------------------------------------------------------------------------- tally groups --
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-  for (int k = 0; k < kTotCount; ++k) g.last_stats[k] = g.h_totals[k];
-  g.last_stats[5] = g.launches - launches0;
-  float kernel_ms = 0.0f;
-  CU_FATAL(cudaEventElapsedTime(&kernel_ms, g.ev_mid, g.ev_end));
-  g.last_stats[6] = (uint64_t)((double)kernel_ms * 1.0e6);  // history kernel, ns on the stream
-  CU_FATAL(cudaEventElapsedTime(&kernel_ms, g.ev_begin, g.ev_mid));
-  g.last_stats[7] = (uint64_t)((double)kernel_ms * 1.0e6);  // sort phase, ns
-  *facet_events += g.h_totals[kTotFacets];          // omp3/neutral.c:202
-  *collision_events += g.h_totals[kTotCollisions];  // omp3/neutral.c:203
-  if (g.opt_print) {
-    printf("Particles  %llu\n", (unsigned long long)g.h_totals[kTotProcessed]);  // :205
+// Slab of one rank: SyncBlock | delta x 3 | owned | (NCCL flavour: tmp | gathered).
+void group_layout(TallyGroup& g) {
+  g.chunk = (g.ncells + g.nranks - 1) / g.nranks;
+  g.chunk = (g.chunk + 1) & ~(size_t)1;  // even: 16-byte vector accesses never straddle slices
+  g.padded = g.chunk * g.nranks;
+  g.slab_bytes = align256(sizeof(SyncBlock)) + kDeltaBuffers * align256(g.padded * 8) +
+                 align256(g.chunk * 8);
+  if (!g.collective) g.slab_bytes += align256(g.chunk * 8) + align256(g.padded * 8);
+}
+
+void group_bind(TallyGroup& g, GroupMember& m, char* base) {
+  m.slab = base;
+  char* p = base;
+  m.sync = (SyncBlock*)p; p += align256(sizeof(SyncBlock));
+  for (int k = 0; k < kDeltaBuffers; ++k) { m.delta[k] = (double*)p; p += align256(g.padded * 8); }
+  m.owned = (double*)p; p += align256(g.chunk * 8);
+  if (!g.collective) {
+    m.tmp = (double*)p; p += align256(g.chunk * 8);
+    m.gathered = (double*)p;
   }
+}
+
+// Allocates the local member `rank` on device `dev` (made current by the caller).
+void group_alloc_member(TallyGroup& g, int rank, int dev) {
+  GroupMember& m = g.m[rank];
+  m.dev = dev;
+  char* base = nullptr;
+  CU_FATAL(cudaMalloc(&base, g.slab_bytes));
+  CU_FATAL(cudaMemset(base, 0, g.slab_bytes));
+  group_bind(g, m, base);
+  int lo = 0, hi = 0;
+  CU_FATAL(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  // the collective of timestep t runs beside the transport of timestep t+1: let its (few,
+  // small) CTAs in whenever an SM has room
+  CU_FATAL(cudaStreamCreateWithPriority(&m.side, cudaStreamNonBlocking, hi));
+  for (int k = 0; k < kDeltaBuffers; ++k) {
+    CU_FATAL(cudaEventCreateWithFlags(&m.ev_hist[k], cudaEventDisableTiming));
+    CU_FATAL(cudaEventCreateWithFlags(&m.ev_zeroed[k], cudaEventDisableTiming));
+  }
+  CU_FATAL(cudaEventCreateWithFlags(&m.ev_side, cudaEventDisableTiming));
+}
+
+void group_free(TallyGroup* g) {
+  if (!g) return;
+  g_groups.erase(std::remove(g_groups.begin(), g_groups.end(), g), g_groups.end());
+  const NcclApi* api = g->collective ? nullptr : nccl_api(nullptr);
+  for (int r = 0; r < g->nranks; ++r) {
+    GroupMember& m = g->m[r];
+    if (m.dev >= 0) {
+      DeviceGuard guard(m.dev);
+      cudaDeviceSynchronize();
+      if (m.comm && api) api->CommDestroy(m.comm);
+      if (m.side) cudaStreamDestroy(m.side);
+      for (int k = 0; k < kDeltaBuffers; ++k) {
+        if (m.ev_hist[k]) cudaEventDestroy(m.ev_hist[k]);
+        if (m.ev_zeroed[k]) cudaEventDestroy(m.ev_zeroed[k]);
+      }
+      if (m.ev_side) cudaEventDestroy(m.ev_side);
+      cudaFree(m.slab);
+    } else if (m.ipc_opened) {
+      cudaIpcCloseMemHandle(m.slab);
+    }
+  }
+  delete g;
+}
+
+// Single-process group over the shards' devices: slabs, peer access, (optionally) NCCL.
+TallyGroup* group_create_local(const Bank* bank, size_t ncells) {
+  TallyGroup* g = new TallyGroup();
+  g->nranks = (int)bank->shards.size();
+  g->ncells = ncells;
+  g->collective = opt_of(bank, &Options::collective);
+  g->reduce_ctas = opt_of(bank, &Options::reduce_ctas);
+  if (g->collective) {  // the peer-memory kernel needs every pair of GPUs peer-mapped
+    for (const Shard& a : bank->shards)
+      for (const Shard& b : bank->shards) {
+        if (a.dev == b.dev) continue;
+        int can = 0;
+        CU_FATAL(cudaDeviceCanAccessPeer(&can, a.dev, b.dev));
+        if (!can) g->collective = 0;
+      }
+    if (!g->collective)
+      fprintf(stderr, "neutral_b200: GPUs are not all peer-accessible: the tally collective "
+                      "falls back to NCCL\n");
+  }
+  group_layout(*g);
+  for (int r = 0; r < g->nranks; ++r) {
+    DeviceGuard guard(bank->shards[r].dev);
+    ctx_on(bank->shards[r].dev);
+    group_alloc_member(*g, r, bank->shards[r].dev);
+  }
+  if (g->collective) {
+    for (int r = 0; r < g->nranks; ++r) {
+      DeviceGuard guard(g->m[r].dev);
+      for (int q = 0; q < g->nranks; ++q) {
+        if (q == r) continue;
+        const cudaError_t err = cudaDeviceEnablePeerAccess(g->m[q].dev, 0);
+        if (err != cudaSuccess && err != cudaErrorPeerAccessAlreadyEnabled)
+          terminate("cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", g->m[r].dev, g->m[q].dev,
+                    cudaGetErrorString(err));
+        (void)cudaGetLastError();
+      }
+    }
+  } else {
+    std::string why;
+    const NcclApi* api = nccl_api(&why);
+    if (!api) terminate("the NCCL flavour of the tally collective was asked for, but %s", why.c_str());
+    nccl_comm_t comms[kMaxRanks];
+    int devs[kMaxRanks];
+    for (int r = 0; r < g->nranks; ++r) devs[r] = g->m[r].dev;
+    NCCL_FATAL(api, api->CommInitAll(comms, g->nranks, devs));
+    for (int r = 0; r < g->nranks; ++r) g->m[r].comm = comms[r];
+  }
+  g_groups.push_back(g);
+  return g;
+}
+
+GroupView group_view(const TallyGroup& g, int rank, int k, bool owned_slices) {
+  GroupView v{};
+  v.nranks = g.nranks;
+  v.rank = rank;
+  v.chunk = g.chunk;
+  v.ncells = g.ncells;
+  for (int d = 0; d < g.nranks; ++d) {
+    v.src[d] = owned_slices ? g.m[d].owned : g.m[d].delta[k];
+    v.sync[d] = g.m[d].sync;
+  }
+  return v;
+}
+
+// The collective half of epoch `epoch` for every LOCAL member, queued on the members' side
+// streams behind their history kernels (ev_hist): reduce-scatter of the delta fused with the
+// fold into the owned slice, then the delta buffer is cleared for its reuse in three epochs.
+void group_enqueue_collective(TallyGroup& g, unsigned long long epoch) {
+  const int k = (int)(epoch % kDeltaBuffers);
+  const NcclApi* api = g.collective ? nullptr : nccl_api(nullptr);
+  for (int r = 0; r < g.nranks; ++r) {
+    GroupMember& m = g.m[r];
+    if (m.dev < 0) continue;
+    DeviceGuard guard(m.dev);
+    CU_FATAL(cudaStreamWaitEvent(m.side, m.ev_hist[k], 0));
+  }
+  if (g.collective) {
+    for (int r = 0; r < g.nranks; ++r) {
+      GroupMember& m = g.m[r];
+      if (m.dev < 0) continue;
+      DeviceGuard guard(m.dev);
+      DeviceCtx& c = ctx_on(m.dev);
+      c.launches += launch_reduce_fold(group_view(g, r, k, false), m.owned, epoch, g.reduce_ctas,
+                                       m.side);
+      c.launches += launch_wait_zero(m.sync, g.nranks, 0, m.delta[k], g.padded, epoch, m.side);
+      CU_FATAL(cudaGetLastError());
+    }
+  } else {
+    NCCL_FATAL(api, api->GroupStart());
+    for (int r = 0; r < g.nranks; ++r) {
+      GroupMember& m = g.m[r];
+      if (m.dev < 0) continue;
+      DeviceGuard guard(m.dev);
+      NCCL_FATAL(api, api->ReduceScatter(m.delta[k], m.tmp, g.chunk, kNcclDouble, kNcclSum, m.comm,
+                                         m.side));
+    }
+    NCCL_FATAL(api, api->GroupEnd());
+    for (int r = 0; r < g.nranks; ++r) {
+      GroupMember& m = g.m[r];
+      if (m.dev < 0) continue;
+      DeviceGuard guard(m.dev);
+      DeviceCtx& c = ctx_on(m.dev);
+      c.launches += launch_fold_plain(m.owned, m.tmp, g.chunk, m.side);
+      // the send buffer is free as soon as the collective has completed on this stream
+      CU_FATAL(cudaMemsetAsync(m.delta[k], 0, g.padded * 8, m.side));
+    }
+  }
+  for (int r = 0; r < g.nranks; ++r) {
+    GroupMember& m = g.m[r];
+    if (m.dev < 0) continue;
+    DeviceGuard guard(m.dev);
+    CU_FATAL(cudaEventRecord(m.ev_zeroed[k], m.side));
+    m.zeroed_recorded[k] = true;
+  }
+  g.dirty = true;
+}
+
+void group_check_fault(TallyGroup& g) {
+  for (int r = 0; r < g.nranks; ++r) {
+    GroupMember& m = g.m[r];
+    if (m.dev < 0) continue;
+    DeviceGuard guard(m.dev);
+    SyncBlock sb;
+    CU_FATAL(cudaMemcpy(&sb, m.sync, sizeof(SyncBlock), cudaMemcpyDeviceToHost));
+    if (sb.fault)
+      terminate("tally collective: rank %d waited more than %llu s for a peer (every rank must "
+                "run the same timesteps and tally syncs)", r, kWaitTimeoutNs / 1000000000ull);
+  }
+}
+
+// Brings the caller-visible tally up to date: target[i] += owned slices, owned = 0
+// (an all-gather fused with the accumulation). Synchronous. In a multi-process group it is a
+// collective: every rank must call it the same number of times.
+void group_flush(TallyGroup& g) {
+  if (!g.dirty || !g.target) return;
+  const NcclApi* api = g.collective ? nullptr : nccl_api(nullptr);
+  const unsigned long long fe = ++g.flush_epoch;
+  const int primary = g.mp ? g.mp_rank : 0;
+  // everything deposited so far must be in the owned slices
+  for (int r = 0; r < g.nranks; ++r) {
+    GroupMember& m = g.m[r];
+    if (m.dev < 0) continue;
+    DeviceGuard guard(m.dev);
+    if (g.mp && g.collective) ctx_on(m.dev).launches += launch_signal(m.sync, 1, fe, m.side);
+    CU_FATAL(cudaStreamSynchronize(m.side));
+  }
+  if (g.collective) {
+    GroupMember& m = g.m[primary];
+    DeviceGuard guard(m.dev);
+    DeviceCtx& c = ctx_on(m.dev);
+    c.launches += launch_gather_owned(group_view(g, primary, 0, true), g.target, g.mp ? fe : 0,
+                                      m.side);
+    if (g.mp) {
+      c.launches += launch_wait_zero(m.sync, g.nranks, 1, m.owned, g.chunk, fe, m.side);
+      CU_FATAL(cudaStreamSynchronize(m.side));
+    } else {
+      CU_FATAL(cudaStreamSynchronize(m.side));
+      for (int r = 0; r < g.nranks; ++r) {
+        DeviceGuard gr(g.m[r].dev);
+        CU_FATAL(cudaMemsetAsync(g.m[r].owned, 0, g.chunk * 8, g.m[r].side));
+        CU_FATAL(cudaStreamSynchronize(g.m[r].side));
+      }
+    }
+  } else {
+    NCCL_FATAL(api, api->GroupStart());
+    for (int r = 0; r < g.nranks; ++r) {
+      GroupMember& m = g.m[r];
+      if (m.dev < 0) continue;
+      DeviceGuard guard(m.dev);
+      NCCL_FATAL(api, api->AllGather(m.owned, m.gathered, g.chunk, kNcclDouble, m.comm, m.side));
+    }
+    NCCL_FATAL(api, api->GroupEnd());
+    for (int r = 0; r < g.nranks; ++r) {
+      GroupMember& m = g.m[r];
+      if (m.dev < 0) continue;
+      DeviceGuard guard(m.dev);
+      if (r == primary) ctx_on(m.dev).launches += launch_fold_plain(g.target, m.gathered, g.ncells, m.side);
+      CU_FATAL(cudaMemsetAsync(m.owned, 0, g.chunk * 8, m.side));
+      CU_FATAL(cudaStreamSynchronize(m.side));
+    }
+  }
+  g.dirty = false;
+  group_check_fault(g);
+}
+
+// Any library-mediated look at memory that a group's unflushed contributions belong to
+// flushes first (validate, copy_buffer, the nb200_memcpy / memset helpers).
+void flush_groups_touching(const void* ptr, size_t bytes) {
+  for (TallyGroup* g : g_groups) {
+    if (!g->dirty || !g->target) continue;
+    const char* lo = (const char*)g->target;
+    const char* hi = lo + g->ncells * 8;
+    const char* p = (const char*)ptr;
+    if (p < hi && p + bytes > lo) group_flush(*g);
+  }
+}
+
+// Replica of a read-only input that lives on `primary_dev`, for device c (current).
+const double* replica_of(DeviceCtx& c, int primary_dev, const double* src, size_t count) {
+  if (c.device == primary_dev || !src) return src;
+  const size_t bytes = count * sizeof(double);
+  for (auto& r : c.replicas)
+    if (r.src == src && r.bytes == bytes) {
+      if (r.generation != g_replica_generation) {
+        CU_FATAL(cudaMemcpyPeerAsync(r.copy, c.device, src, primary_dev, bytes, c.stream));
+        r.generation = g_replica_generation;
+      }
+      return (const double*)r.copy;
+    }
+  void* copy = nullptr;
+  CU_FATAL(cudaMalloc(&copy, bytes ? bytes : 8));
+  // the primary's uploads went through its own stream: make sure they have landed
+  {
+    DeviceGuard guard(primary_dev);
+    CU_FATAL(cudaStreamSynchronize(ctx_on(primary_dev).stream));
+  }
+  CU_FATAL(cudaMemcpyPeerAsync(copy, c.device, src, primary_dev, bytes, c.stream));
+  c.replicas.push_back({src, bytes, copy, g_replica_generation});
+  return (const double*)copy;
+}
+
+// --------------------------------------------------------------------- timestep pipeline --
+void finish_oldest(Bank* bank, uint64_t* facet_events, uint64_t* collision_events);
+
+// First half of a timestep: everything is enqueued, nothing is waited for.
+void enqueue_step(Bank* bank, const StepRequest& rq) {
+  if ((int)bank->pending.size() >= kMaxPending)
+    terminate("solve_transport_2d: %d timesteps of this bank are enqueued and not collected "
+              "(defer_finish=1): call nb200_solve_finish", kMaxPending);
+  const size_t ncells = (size_t)rq.nx * rq.ny;
+  TallyGroup* group = nullptr;
+  if (!single_shard(bank)) {
+    if (bank->group && bank->group->ncells != ncells) {  // another mesh: start over
+      group_flush(*bank->group);
+      group_free(bank->group);
+      bank->group = nullptr;
+    }
+    if (!bank->group) bank->group = group_create_local(bank, ncells);
+    group = bank->group;
+  } else if (g_mp && g_mp->m[g_mp->mp_rank].dev == bank->shards[0].dev) {
+    group = g_mp;
+    if (group->ncells != ncells)
+      terminate("solve_transport_2d: the multi-process group was created for %zu cells, the "
+                "mesh has %zu", group->ncells, ncells);
+  }
+  unsigned long long epoch = 0;
+  int k = 0;
+  if (group) {
+    if (group->target != rq.tally) {  // a different caller tally: settle the old one first
+      group_flush(*group);
+      group->target = rq.tally;
+      group->target_dev = bank->primary_dev;
+    }
+    epoch = ++group->epoch;
+    k = (int)(epoch % kDeltaBuffers);
+  }
+  PendingStep ps;
+  ps.pipeline = opt_of(bank, &Options::pipeline) != 0;
+  ps.print = opt_of(bank, &Options::print) != 0;
+  ps.master_key = rq.master_key;
+  uint64_t launches0 = 0;
+  for (const Shard& sh : bank->shards) launches0 += ctx_on(sh.dev).launches;
+  ps.launches0 = launches0;
+  for (size_t si = 0; si < bank->shards.size(); ++si) {
+    Shard& sh = bank->shards[si];
+    DeviceGuard guard(sh.dev);
+    DeviceCtx& c = ctx_on(sh.dev);
+    const int slot = take_slot(c);
+    ps.slot[si] = slot;
+    ShardIO io;
+    const int pd = bank->primary_dev;
+    io.density = replica_of(c, pd, rq.density, ncells);
+    io.edgex = replica_of(c, pd, rq.edgex, (size_t)rq.nx + 1);
+    io.edgey = replica_of(c, pd, rq.edgey, (size_t)rq.ny + 1);
+    io.s_keys = replica_of(c, pd, rq.s_keys, (size_t)rq.s_n);
+    io.s_vals = replica_of(c, pd, rq.s_vals, (size_t)rq.s_n);
+    io.a_keys = replica_of(c, pd, rq.a_keys, (size_t)rq.a_n);
+    io.a_vals = replica_of(c, pd, rq.a_vals, (size_t)rq.a_n);
+    io.tally = rq.tally;
+    // per-particle counters live on the primary GPU, indexed in injection order: a secondary
+    // shard reaches its part of them through peer access (one 8-byte update per particle-step)
+    const bool counters_ok = sh.dev == pd || (group && group->collective);
+    io.r0 = rq.r0 && counters_ok ? rq.r0 + sh.first : nullptr;
+    io.r1 = rq.r1 && counters_ok ? rq.r1 + sh.first : nullptr;
+    io.r2 = rq.r2 && counters_ok ? rq.r2 + sh.first : nullptr;
+    SyncBlock* sync = nullptr;
+    if (group) {
+      const int rank = group->mp ? group->mp_rank : (int)si;
+      GroupMember& m = group->m[rank];
+      io.tally = m.delta[k];
+      if (group->collective) sync = m.sync;
+      // the buffer was cleared behind its last collective, on the side stream
+      if (m.zeroed_recorded[k]) CU_FATAL(cudaStreamWaitEvent(c.stream, m.ev_zeroed[k], 0));
+      enqueue_shard_step(c, bank, sh, rq, io, slot, sync, epoch);
+      CU_FATAL(cudaEventRecord(m.ev_hist[k], c.stream));
+    } else {
+      enqueue_shard_step(c, bank, sh, rq, io, slot, nullptr, 0);
+    }
+  }
+  if (group) group_enqueue_collective(*group, epoch);
+  bank->pending.push_back(ps);
+  g_last_deferred = bank;
+}
+
+// Second half of a timestep: waits for the streams, checks the device-side faults, updates
+// the live-prefix bounds and hands the counts to the caller (omp3/neutral.c:202-205).
+void finish_oldest(Bank* bank, uint64_t* facet_events, uint64_t* collision_events) {
+  if (bank->pending.empty()) return;
+  const PendingStep ps = bank->pending.front();
+  bank->pending.pop_front();
+  uint64_t tot[kTotCount] = {0};
+  uint64_t launches1 = 0;
+  double hist_ms = 0.0, sort_ms = 0.0;
+  for (size_t si = 0; si < bank->shards.size(); ++si) {
+    Shard& sh = bank->shards[si];
+    DeviceGuard guard(sh.dev);
+    DeviceCtx& c = ctx_on(sh.dev);
+    const int slot = ps.slot[si];
+    // wait for THIS step's totals only: later timesteps may already be queued behind it
+    CU_FATAL(cudaEventSynchronize(c.ev_pub[slot]));
+    const volatile unsigned long long* h = c.h_totals + (size_t)slot * kTotCount;
+    if (h[kTotFault])
+      terminate("solve_transport_2d: a cross-section table's energy grid is not strictly "
+                "increasing (omp3/neutral.c:506-511 assumes it is)");
+    if (h[kTotGroupFault])
+      terminate("solve_transport_2d: the tally collective timed out waiting for a peer GPU");
+    // The sort compacted every particle that was dead at the start of this step behind the
+    // live prefix; particles that died DURING the step still sit inside the prefix (the next
+    // sort moves them out), so the prefix to visit next is this step's live count.
+    if (ps.pipeline) sh.n_upper = std::min(sh.n_upper, (int)h[kTotProcessed]);
+    for (int t = 0; t <= kTotDeaths; ++t) tot[t] += h[t];
+    float ms = 0.0f;
+    CU_FATAL(cudaEventElapsedTime(&ms, c.ev_mid[slot], c.ev_end[slot]));
+    hist_ms = std::max(hist_ms, (double)ms);
+    CU_FATAL(cudaEventElapsedTime(&ms, c.ev_begin[slot], c.ev_mid[slot]));
+    sort_ms = std::max(sort_ms, (double)ms);
+    memset((void*)(c.h_totals + (size_t)slot * kTotCount), 0, sizeof(unsigned long long) * kTotCount);
+    c.slot_busy[slot] = false;
+    c.pending_steps--;
+    launches1 += c.launches;
+  }
+  for (int t = 0; t <= kTotDeaths; ++t) g_last_stats[t] = tot[t];
+  g_last_stats[5] = launches1 - ps.launches0;
+  g_last_stats[6] = (uint64_t)(hist_ms * 1.0e6);  // history kernel, ns on the stream (max over GPUs)
+  g_last_stats[7] = (uint64_t)(sort_ms * 1.0e6);  // sort phase, ns
+  if (g_step_log.size() < 100000)
+    g_step_log.push_back({ps.master_key, tot[kTotFacets], tot[kTotCollisions], tot[kTotProcessed],
+                          tot[kTotCensus], tot[kTotDeaths], g_last_stats[6], g_last_stats[7],
+                          (int)bank->shards.size()});
+  if (facet_events) *facet_events += tot[kTotFacets];            // omp3/neutral.c:202
+  if (collision_events) *collision_events += tot[kTotCollisions];  // omp3/neutral.c:203
+  if (ps.print) printf("Particles  %llu\n", (unsigned long long)tot[kTotProcessed]);  // :205
+  if (bank->pending.empty()) refresh_mirror(bank);
+}
+
+void finish_all(Bank* bank) {
+  while (!bank->pending.empty()) finish_oldest(bank, nullptr, nullptr);
 }
 
 void check_boundary_args(const char* who, int nx, int ny, int global_nx, int global_ny,
@@ -644,20 +1211,55 @@ __global__ void k_partial_sums(const double* __restrict__ v, size_t n, double* p
   }
 }
 
-double device_sum(const double* v, size_t n) {
+double device_sum(DeviceCtx& c, const double* v, size_t n) {
   const int blocks = 592, threads = 256;
   double* d_partial = nullptr;
   CU_FATAL(cudaMalloc(&d_partial, sizeof(double) * blocks));
-  k_partial_sums<<<blocks, threads, 0, g.stream>>>(v, n, d_partial);
-  g.launches++;
+  k_partial_sums<<<blocks, threads, 0, c.stream>>>(v, n, d_partial);
+  c.launches++;
   std::vector<double> h(blocks);
   CU_FATAL(cudaMemcpyAsync(h.data(), d_partial, sizeof(double) * blocks,
-                           cudaMemcpyDeviceToHost, g.stream));
-  CU_FATAL(cudaStreamSynchronize(g.stream));
+                           cudaMemcpyDeviceToHost, c.stream));
+  CU_FATAL(cudaStreamSynchronize(c.stream));
   cudaFree(d_partial);
   double s = 0.0;
   for (double x : h) s += x;
   return s;
+}
+
+// The machine-readable side of `validate`: written when NB200_RESULTS_JSON
+// names a file. Same verdict as the printed lines, plus what the library saw of the run.
+void write_results_json(const char* path, const char* deck, int nx, int ny, double total,
+                        bool have_expected, double expected, const char* verdict) {
+  FILE* fp = fopen(path, "w");
+  if (!fp) {
+    fprintf(stderr, "neutral_b200: cannot write %s\n", path);
+    return;
+  }
+  cudaDeviceProp prop{};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaGetDeviceProperties(&prop, dev);
+  fprintf(fp, "{\"deck\": \"%s\", \"nx\": %d, \"ny\": %d, \"device\": \"%s\",\n", deck, nx, ny,
+          prop.name);
+  fprintf(fp, " \"tally_total\": %.17e, ", total);
+  if (have_expected)
+    fprintf(fp, "\"expected\": %.17e, \"relative_error\": %.6e, \"tolerance\": 1e-3, ", expected,
+            fabs(expected - total) / (fabs(expected) > 0.0 ? fabs(expected) : 1.0));
+  else
+    fprintf(fp, "\"expected\": null, ");
+  fprintf(fp, "\"verdict\": \"%s\",\n \"steps\": [", verdict);
+  for (size_t i = 0; i < g_step_log.size(); ++i) {
+    const StepLog& s = g_step_log[i];
+    fprintf(fp, "%s\n  {\"facets\": %llu, \"collisions\": %llu, \"particles\": %llu, \"census\": %llu, "
+                "\"deaths\": %llu, \"history_kernel_ns\": %llu, \"sort_phase_ns\": %llu, \"gpus\": %d}",
+            i ? "," : "", (unsigned long long)s.facets, (unsigned long long)s.collisions,
+            (unsigned long long)s.processed, (unsigned long long)s.census,
+            (unsigned long long)s.deaths, (unsigned long long)s.history_ns,
+            (unsigned long long)s.sort_ns, s.ngpus);
+  }
+  fprintf(fp, "\n ]}\n");
+  fclose(fp);
 }
 
 }  // namespace
@@ -679,16 +1281,38 @@ extern "C" void solve_transport_2d(
     printf("Out of particles\n");
     return;
   }
-  require_ready();
+  ctx_required();
   check_boundary_args("solve_transport_2d", nx, ny, global_nx, global_ny, pad, x_off, y_off);
   Bank* bank = bank_of(particles);
   if (!bank) terminate("solve_transport_2d: `particles` is not a bank created by this "
                        "kernel set's inject_particles / nb200_bank_create");
-  run_step(bank, nx, ny, master_key, dt, ntotal_particles, density, edgex, edgey,
-           cs_scatter_table->keys, cs_scatter_table->values, cs_scatter_table->nentries,
-           cs_absorb_table->keys, cs_absorb_table->values, cs_absorb_table->nentries,
-           energy_deposition_tally, reduce_array0, reduce_array1, reduce_array2,
-           facet_events, collision_events);
+  const bool defer = opt_of(bank, &Options::defer_finish) != 0;
+  if (!defer && !bank->pending.empty())
+    terminate("solve_transport_2d: earlier timesteps of this bank were enqueued with "
+              "defer_finish=1 and nb200_solve_finish has not collected them");
+  StepRequest rq;
+  rq.nx = nx;
+  rq.ny = ny;
+  rq.master_key = master_key;
+  rq.dt = dt;
+  rq.ntotal = ntotal_particles;
+  rq.density = density;
+  rq.edgex = edgex;
+  rq.edgey = edgey;
+  rq.s_keys = cs_scatter_table->keys;
+  rq.s_vals = cs_scatter_table->values;
+  rq.s_n = cs_scatter_table->nentries;
+  rq.a_keys = cs_absorb_table->keys;
+  rq.a_vals = cs_absorb_table->values;
+  rq.a_n = cs_absorb_table->nentries;
+  rq.tally = energy_deposition_tally;
+  rq.r0 = reduce_array0;
+  rq.r1 = reduce_array1;
+  rq.r2 = reduce_array2;
+  enqueue_step(bank, rq);
+  // "defer_finish": the caller keeps the GPU fed (the next timestep, its own host work) and
+  // collects the counts later with nb200_solve_finish
+  if (!defer) finish_oldest(bank, facet_events, collision_events);
 }
 
 extern "C" size_t inject_particles(
@@ -698,26 +1322,36 @@ extern "C" size_t inject_particles(
     const double local_particle_height, const int x_off, const int y_off, const double dt,
     const double* edgex, const double* edgey, const double initial_energy,
     nb200_particle_soa** particles) {
-  require_ready();
+  DeviceCtx& primary = ctx_required();
   check_boundary_args("inject_particles", local_nx, local_ny, global_nx, local_ny, pad, x_off,
                       y_off);
-  const int first = g.shard_count >= 0 ? g.shard_first : 0;
-  const int count = g.shard_count >= 0 ? g.shard_count : nparticles;
+  const int first = g_shard_count >= 0 ? g_shard_first : 0;
+  const int count = g_shard_count >= 0 ? g_shard_count : nparticles;
   if (first < 0 || first + count > nparticles)
     terminate("inject_particles: shard [%d, %d) outside [0, %d)", first, first + count,
               nparticles);
 
-  if (g.opt_device_inject) {
+  size_t bytes = 0;
+  Bank* bank = new_bank(count, (uint64_t)first, g_opt.ngpus, g_opt.headroom_pct,
+                        g_opt.host_mirror != 0, &bytes);
+  if (g_opt.device_inject) {
     // The bank is generated where it lives: no host loop, no 80-byte-per-particle upload.
-    size_t bytes = 0;
-    BankHandle* h = new_handle(count, (uint64_t)first, &bytes);
-    InjectArgs ia{edgex, edgey, local_nx, local_ny, local_particle_left_off,
-                  local_particle_bottom_off, local_particle_width, local_particle_height, dt,
-                  initial_energy};
-    g.launches += launch_inject(h->impl->cur, count, (uint64_t)first, ia, g.d_sct, g.stream);
-    CU_FATAL(cudaGetLastError());
-    CU_FATAL(cudaStreamSynchronize(g.stream));
-    *particles = &h->view;
+    for (Shard& sh : bank->shards) {
+      DeviceGuard guard(sh.dev);
+      DeviceCtx& c = ctx_on(sh.dev);
+      InjectArgs ia{replica_of(c, primary.device, edgex, (size_t)local_nx + 1),
+                    replica_of(c, primary.device, edgey, (size_t)local_ny + 1), local_nx,
+                    local_ny, local_particle_left_off, local_particle_bottom_off,
+                    local_particle_width, local_particle_height, dt, initial_energy};
+      c.launches += launch_inject(sh.cur, sh.n, sh.pid0, ia, c.d_sct, c.stream);
+      CU_FATAL(cudaGetLastError());
+    }
+    for (Shard& sh : bank->shards) {
+      DeviceGuard guard(sh.dev);
+      CU_FATAL(cudaStreamSynchronize(ctx_on(sh.dev).stream));
+    }
+    refresh_mirror(bank);
+    *particles = handle_of(bank);
     return bytes;
   }
 
@@ -765,53 +1399,58 @@ extern "C" size_t inject_particles(
     dead[s] = 0;
   }
 
-  size_t bytes = 0;
-  BankHandle* h = new_handle(count, (uint64_t)first, &bytes);
   SoaView host{x.data(), y.data(), ox.data(), oy.data(), en.data(), wt.data(), dtc.data(),
                mfp.data(), cx.data(), cy.data(), dead.data()};
-  upload_host_soa(host, count, h->impl->cur);
-  *particles = &h->view;
+  upload_host_soa(bank, host);
+  refresh_mirror(bank);
+  *particles = handle_of(bank);
   return bytes;
 }
 
 extern "C" void validate(const int nx, const int ny, const char* params_filename,
                          const int rank, double* energy_tally) {
-  require_ready();
-  const double total = device_sum(energy_tally, (size_t)nx * ny);
+  DeviceCtx& c = ctx_required();
+  flush_groups_touching(energy_tally, sizeof(double) * (size_t)nx * ny);
+  const double total = device_sum(c, energy_tally, (size_t)nx * ny);
   if (rank != 0) return;
   printf("\nFinal global_energy_tally %.15e\n", total);
   double expected = 0.0;
+  const char* json = getenv("NB200_RESULTS_JSON");
   if (!find_expected("problems/neutral.tests", params_filename, &expected)) {
     printf("Warning. Test entry was not found, could NOT validate.\n");
+    if (json && *json)
+      write_results_json(json, params_filename, nx, ny, total, false, 0.0, "NOT_VALIDATED");
     return;
   }
   printf("Expected %.12e, result was %.12e.\n", expected, total);
+  // arch's within_tolerance is not in the reference tree; archlite's (and this) reading of it
+  // is the relative difference against VALIDATE_TOLERANCE (neutral_data.h:27)
   const double scale = fabs(expected) > 0.0 ? fabs(expected) : 1.0;
-  if (fabs(expected - total) / scale < 1.0e-3) {  // VALIDATE_TOLERANCE, neutral_data.h:27
-    printf("PASSED validation.\n");
-  } else {
-    printf("FAILED validation.\n");
-  }
+  const bool pass = fabs(expected - total) / scale < 1.0e-3;
+  printf(pass ? "PASSED validation.\n" : "FAILED validation.\n");
+  if (json && *json)
+    write_results_json(json, params_filename, nx, ny, total, true, expected,
+                       pass ? "PASSED" : "FAILED");
 }
 
 // ======================================================================================
 // 2. allocation layer
 // ======================================================================================
-extern "C" size_t allocate_data(double** buf, size_t len) { return device_zalloc(buf, len); }
-extern "C" size_t allocate_float_data(float** buf, size_t len) { return device_zalloc(buf, len); }
-extern "C" size_t allocate_int_data(int** buf, size_t len) { return device_zalloc(buf, len); }
+extern "C" size_t allocate_data(double** buf, size_t len) { return device_zalloc(ctx_required(), buf, len); }
+extern "C" size_t allocate_float_data(float** buf, size_t len) { return device_zalloc(ctx_required(), buf, len); }
+extern "C" size_t allocate_int_data(int** buf, size_t len) { return device_zalloc(ctx_required(), buf, len); }
 extern "C" size_t allocate_uint64_data(uint64_t** buf, size_t len) {
-  return device_zalloc(buf, len);
+  return device_zalloc(ctx_required(), buf, len);
 }
 
 extern "C" void allocate_host_data(double** buf, size_t len) {
-  require_ready();
+  ctx_required();
   CU_FATAL(cudaMallocHost((void**)buf, sizeof(double) * (len ? len : 1)));
   memset(*buf, 0, sizeof(double) * len);
 }
 
 extern "C" void allocate_host_float_data(float** buf, size_t len) {
-  require_ready();
+  ctx_required();
   CU_FATAL(cudaMallocHost((void**)buf, sizeof(float) * (len ? len : 1)));
   memset(*buf, 0, sizeof(float) * len);
 }
@@ -820,16 +1459,20 @@ extern "C" void deallocate_data(double* buf) { cudaFree(buf); }
 extern "C" void deallocate_host_data(double* buf) { cudaFreeHost(buf); }
 
 extern "C" void copy_buffer(const size_t len, double** src, double** dst, int send) {
-  require_ready();
-  CU_FATAL(cudaMemcpyAsync(*dst, *src, sizeof(double) * len,
-                           send ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, g.stream));
-  CU_FATAL(cudaStreamSynchronize(g.stream));
+  DeviceCtx& c = ctx_required();
+  if (!send) flush_groups_touching(*src, sizeof(double) * len);
+  // cudaMemcpyDefault: the direction follows from the pointers, so a RECV of a buffer that
+  // happens to be host memory (main.c:169-200 hands its own malloc to the VisIt writer) works
+  (void)send;
+  CU_FATAL(cudaMemcpyAsync(*dst, *src, sizeof(double) * len, cudaMemcpyDefault, c.stream));
+  CU_FATAL(cudaStreamSynchronize(c.stream));
 }
 
 extern "C" void move_host_buffer_to_device(const size_t len, double** src, double** dst) {
-  device_zalloc(dst, len);
-  CU_FATAL(cudaMemcpyAsync(*dst, *src, sizeof(double) * len, cudaMemcpyHostToDevice, g.stream));
-  CU_FATAL(cudaStreamSynchronize(g.stream));
+  DeviceCtx& c = ctx_required();
+  device_zalloc(c, dst, len);
+  CU_FATAL(cudaMemcpyAsync(*dst, *src, sizeof(double) * len, cudaMemcpyHostToDevice, c.stream));
+  CU_FATAL(cudaStreamSynchronize(c.stream));
   cudaPointerAttributes attr{};
   if (cudaPointerGetAttributes(&attr, *src) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
     cudaFreeHost(*src);
@@ -845,12 +1488,16 @@ extern "C" void initialise_devices(int rank) {
   if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0)
     terminate("no CUDA device available: the b200 kernel set has no CPU fallback");
   CU_FATAL(cudaSetDevice(rank % count));
-  require_ready();
+  ctx_required();
   cudaDeviceProp prop{};
   CU_FATAL(cudaGetDeviceProperties(&prop, rank % count));
   printf("Rank %d using GPU %d: %s (sm_%d%d, %d SMs, %.0f GB)\n", rank, rank % count, prop.name,
          prop.major, prop.minor, prop.multiProcessorCount,
          (double)prop.totalGlobalMem / (1024.0 * 1024.0 * 1024.0));
+  if (g_opt.ngpus > 1)
+    printf("Particle bank sharded over %d GPUs (NB200_NGPUS), tally combined by the %s\n",
+           g_opt.ngpus, g_opt.collective ? "library's peer-memory reduce-scatter kernel"
+                                         : "NCCL reduce-scatter");
 }
 
 // ======================================================================================
@@ -872,7 +1519,7 @@ extern "C" void nb200_solve_transport_2d_host(
     printf("Out of particles\n");
     return;
   }
-  require_ready();
+  DeviceCtx& c = ctx_required();
   check_boundary_args("nb200_solve_transport_2d_host", nx, ny, global_nx, global_ny, pad,
                       x_off, y_off);
   const size_t ncells = (size_t)nx * ny;
@@ -881,7 +1528,7 @@ extern "C" void nb200_solve_transport_2d_host(
   auto upload = [&](const void* host, size_t bytes) {
     void* d = nullptr;
     CU_FATAL(cudaMalloc(&d, bytes ? bytes : 1));
-    CU_FATAL(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, g.stream));
+    CU_FATAL(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, c.stream));
     return d;
   };
   double* d_density = (double*)upload(density, sizeof(double) * ncells);
@@ -898,43 +1545,59 @@ extern "C" void nb200_solve_transport_2d_host(
   for (int k = 0; k < 3; ++k)
     if (h_r[k]) d_r[k] = (uint64_t*)upload(h_r[k], sizeof(uint64_t) * (size_t)n);
 
+  // fresh device addresses every call: the per-pointer scheduling hints must not go stale on
+  // recycled addresses (they would still be harmless, but they would be worthless)
+  c.table_cache.clear();
+  c.mesh_cache.clear();
   Bank bank;
   bank.n = n;
-  bank.n_upper = n;
   bank.pid0 = 0;
-  bank_alloc(bank.cur, n);
-  g.launches += launch_import_aos(bank.cur, d_aos, n, g.stream);
-  g.cs_s_keys = nullptr;  // fresh uploads: never trust the cached table inspection
-  run_step(&bank, nx, ny, master_key, dt, ntotal_particles, d_density, d_edgex, d_edgey, d_sk,
-           d_sv, s_n, d_ak, d_av, a_n, d_tally, d_r[0], d_r[1], d_r[2], facet_events,
-           collision_events);
-  finish_step(facet_events, collision_events);  // the host flavour never defers (no-op if done)
-  g.cs_s_keys = nullptr;
-  g.launches += launch_export_aos(bank.cur, d_aos, n, g.stream);
+  bank.primary_dev = c.device;
+  bank.overrides.push_back({option_index("defer_finish"), 0});  // the host flavour never defers
+  Shard sh;
+  sh.dev = c.device;
+  sh.n = sh.capacity = sh.n_upper = n;
+  bank_alloc(c, sh.cur, n);
+  bank.shards.push_back(sh);
+  c.launches += launch_import_aos(bank.shards[0].cur, d_aos, n, c.stream);
+  StepRequest rq;
+  rq.nx = nx; rq.ny = ny; rq.master_key = master_key; rq.dt = dt; rq.ntotal = ntotal_particles;
+  rq.density = d_density; rq.edgex = d_edgex; rq.edgey = d_edgey;
+  rq.s_keys = d_sk; rq.s_vals = d_sv; rq.s_n = s_n;
+  rq.a_keys = d_ak; rq.a_vals = d_av; rq.a_n = a_n;
+  rq.tally = d_tally; rq.r0 = d_r[0]; rq.r1 = d_r[1]; rq.r2 = d_r[2];
+  Bank* const was_deferred = g_last_deferred;
+  enqueue_step(&bank, rq);
+  finish_oldest(&bank, facet_events, collision_events);
+  g_last_deferred = was_deferred;
+  Shard& s0 = bank.shards[0];
+  c.launches += launch_export_aos(s0.cur, d_aos, n, c.stream);
   CU_FATAL(cudaMemcpyAsync(particles, d_aos, sizeof(nb200_particle_aos) * (size_t)n,
-                           cudaMemcpyDeviceToHost, g.stream));
+                           cudaMemcpyDeviceToHost, c.stream));
   CU_FATAL(cudaMemcpyAsync(energy_deposition_tally, d_tally, sizeof(double) * ncells,
-                           cudaMemcpyDeviceToHost, g.stream));
+                           cudaMemcpyDeviceToHost, c.stream));
   for (int k = 0; k < 3; ++k)
     if (h_r[k])
       CU_FATAL(cudaMemcpyAsync(h_r[k], d_r[k], sizeof(uint64_t) * (size_t)n,
-                               cudaMemcpyDeviceToHost, g.stream));
-  CU_FATAL(cudaStreamSynchronize(g.stream));
-  bank_release(bank.cur);
-  if (bank.has_alt) {
-    bank_release(bank.alt);
-    cudaFree(bank.keys);
+                               cudaMemcpyDeviceToHost, c.stream));
+  CU_FATAL(cudaStreamSynchronize(c.stream));
+  bank_release(s0.cur);
+  if (s0.has_alt) {
+    bank_release(s0.alt);
+    cudaFree(s0.keys);
   }
   void* to_free[] = {d_density, d_edgex, d_edgey, d_sk, d_sv, d_ak, d_av, d_tally, d_aos,
                      d_r[0], d_r[1], d_r[2]};
   for (void* p : to_free) cudaFree(p);
+  c.table_cache.clear();
+  c.mesh_cache.clear();
 }
 
 // ======================================================================================
 // 4. extensions
 // ======================================================================================
 extern "C" int nb200_abi_version(void) { return NB200_ABI_VERSION; }
-extern "C" const char* nb200_last_error(void) { return g.last_error.c_str(); }
+extern "C" const char* nb200_last_error(void) { return g_last_error.c_str(); }
 
 extern "C" int nb200_device_count(void) {
   int count = 0;
@@ -946,163 +1609,199 @@ extern "C" int nb200_device_count(void) {
 }
 
 extern "C" int nb200_set_stream(void* cuda_stream) {
-  g.stream = (cudaStream_t)cuda_stream;
+  CTX_OR_RETURN(c);
+  if (c.pending_steps > 0) {
+    set_error("nb200_set_stream: %d timestep(s) are still enqueued on the current stream; "
+              "collect them with nb200_solve_finish first", c.pending_steps);
+    return -4;
+  }
+  c.stream = (cudaStream_t)cuda_stream;
   return 0;
 }
 
 extern "C" int nb200_set_shard(int first, int count) {
-  g.shard_first = first;
-  g.shard_count = count;
+  g_shard_first = first;
+  g_shard_count = count;
   return 0;
+}
+
+// A bank operation that rewrites or releases the bank must not race a timestep in flight.
+static int refuse_if_pending(Bank* bank, const char* who) {
+  if (bank->pending.empty()) return 0;
+  set_error("%s: %d timestep(s) of this bank are enqueued and not collected; call "
+            "nb200_solve_finish first", who, (int)bank->pending.size());
+  return -4;
 }
 
 extern "C" int nb200_bank_create(const nb200_particle_soa* host, int count, int pid_first,
                                  nb200_particle_soa** particles) {
-  if (ensure_ready() != 0) return -1;
+  CTX_OR_RETURN(c);
+  (void)c;
   if (!host || !particles || count < 0) {
     set_error("nb200_bank_create: bad arguments");
     return -3;
   }
-  BankHandle* h = new_handle(count, (uint64_t)pid_first, nullptr);
-  if (count > 0) upload_host_soa(as_soa_view(*host), count, h->impl->cur);
-  *particles = &h->view;
+  Bank* bank = new_bank(count, (uint64_t)pid_first, g_opt.ngpus, g_opt.headroom_pct,
+                        g_opt.host_mirror != 0, nullptr);
+  if (count > 0) upload_host_soa(bank, as_soa_view(*host));
+  refresh_mirror(bank);
+  *particles = handle_of(bank);
   return 0;
 }
 
 extern "C" int nb200_bank_upload(nb200_particle_soa* particles, const nb200_particle_soa* host) {
-  if (ensure_ready() != 0) return -1;
+  CTX_OR_RETURN(c0);
+  (void)c0;
   Bank* bank = bank_of(particles);
   if (!bank || !host) {
     set_error("nb200_bank_upload: not a bank handle");
     return -3;
   }
-  if (!bank->has_export) {
-    soa_alloc(bank->exported, bank->n);
-    bank->has_export = true;
-    reinterpret_cast<BankHandle*>(particles)->view = as_public(bank->exported);
+  if (int rc = refuse_if_pending(bank, "nb200_bank_upload")) return rc;
+  for (Shard& sh : bank->shards) {
+    DeviceGuard guard(sh.dev);
+    DeviceCtx& c = ctx_on(sh.dev);
+    ensure_export(c, sh);
+    // The plain SoA view doubles as the staging area: H2D per field, then one repack kernel.
+    const SoaView& s = sh.exported;
+    const SoaView h = soa_offset(as_soa_view(*host), (size_t)sh.first);
+    const size_t n = (size_t)sh.n;
+    const double* hd[] = {h.x, h.y, h.omega_x, h.omega_y, h.energy, h.weight, h.dt_to_census,
+                          h.mfp_to_collision};
+    double* dd[] = {s.x, s.y, s.omega_x, s.omega_y, s.energy, s.weight, s.dt_to_census,
+                    s.mfp_to_collision};
+    for (int k = 0; k < 8; ++k)
+      CU_TRY(cudaMemcpyAsync(dd[k], hd[k], sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+    const int* hi[] = {h.cellx, h.celly, h.dead};
+    int* di[] = {s.cellx, s.celly, s.dead};
+    for (int k = 0; k < 3; ++k)
+      CU_TRY(cudaMemcpyAsync(di[k], hi[k], sizeof(int) * n, cudaMemcpyHostToDevice, c.stream));
+    c.launches += launch_import_soa(sh.cur, s, sh.n, 0, c.stream);
+    sh.n_upper = sh.n;
   }
-  // The plain SoA view doubles as the staging area: H2D per field, then one repack kernel.
-  const SoaView& s = bank->exported;
-  const size_t n = (size_t)bank->n;
-  const double* hd[] = {host->x, host->y, host->omega_x, host->omega_y, host->energy,
-                        host->weight, host->dt_to_census, host->mfp_to_collision};
-  double* dd[] = {s.x, s.y, s.omega_x, s.omega_y, s.energy, s.weight, s.dt_to_census,
-                  s.mfp_to_collision};
-  for (int k = 0; k < 8; ++k)
-    CU_TRY(cudaMemcpyAsync(dd[k], hd[k], sizeof(double) * n, cudaMemcpyHostToDevice, g.stream));
-  const int* hi[] = {host->cellx, host->celly, host->dead};
-  int* di[] = {s.cellx, s.celly, s.dead};
-  for (int k = 0; k < 3; ++k)
-    CU_TRY(cudaMemcpyAsync(di[k], hi[k], sizeof(int) * n, cudaMemcpyHostToDevice, g.stream));
-  g.launches += launch_import_soa(bank->cur, s, bank->n, 0, g.stream);
-  bank->n_upper = bank->n;
+  if (single_shard(bank) && !bank->mirror.present)
+    set_views(bank, as_public(bank->shards[0].exported));
   return 0;
 }
 
 // The plain device SoA view behind the handle (allocated on first use). Together with
 // nb200_bank_import / nb200_bank_export it lets a host move banks with its own asynchronous
-// copies: fill the view, then import; export, then read the view.
+// copies: fill the view, then import; export, then read the view. Single-GPU banks only.
 extern "C" int nb200_bank_view(nb200_particle_soa* particles, nb200_particle_soa* view_out) {
-  if (ensure_ready() != 0) return -1;
+  CTX_OR_RETURN(c0);
+  (void)c0;
   Bank* bank = bank_of(particles);
-  if (!bank || !view_out) {
-    set_error("nb200_bank_view: not a bank handle");
+  if (!bank || !view_out || !single_shard(bank)) {
+    set_error("nb200_bank_view: not a (single-GPU) bank handle");
     return -3;
   }
-  if (!bank->has_export) {
-    soa_alloc(bank->exported, bank->n);
-    bank->has_export = true;
-    reinterpret_cast<BankHandle*>(particles)->view = as_public(bank->exported);
-  }
-  *view_out = as_public(bank->exported);
+  Shard& sh = bank->shards[0];
+  DeviceGuard guard(sh.dev);
+  ensure_export(ctx_on(sh.dev), sh);
+  if (!bank->mirror.present) set_views(bank, as_public(sh.exported));
+  *view_out = as_public(sh.exported);
   return 0;
 }
 
 // Rebuilds the bank from its plain SoA view (asynchronous on the library's stream).
 extern "C" int nb200_bank_import(nb200_particle_soa* particles) {
-  if (ensure_ready() != 0) return -1;
+  CTX_OR_RETURN(c0);
+  (void)c0;
   Bank* bank = bank_of(particles);
-  if (!bank || !bank->has_export) {
-    set_error("nb200_bank_import: not a bank handle, or its view was never requested");
+  if (!bank || !single_shard(bank) || !bank->shards[0].has_export) {
+    set_error("nb200_bank_import: not a (single-GPU) bank handle, or its view was never requested");
     return -3;
   }
-  g.launches += launch_import_soa(bank->cur, bank->exported, bank->n, 0, g.stream);
-  bank->n_upper = bank->n;
+  if (int rc = refuse_if_pending(bank, "nb200_bank_import")) return rc;
+  Shard& sh = bank->shards[0];
+  DeviceGuard guard(sh.dev);
+  DeviceCtx& c = ctx_on(sh.dev);
+  c.launches += launch_import_soa(sh.cur, sh.exported, sh.n, 0, c.stream);
+  sh.n_upper = sh.n;
   return 0;
 }
 
 extern "C" int nb200_accumulate(double* dst_device, const double* src_device, size_t n) {
-  if (ensure_ready() != 0) return -1;
-  g.launches += launch_accumulate(dst_device, src_device, n, g.stream);
+  CTX_OR_RETURN(c);
+  c.launches += launch_accumulate(dst_device, src_device, n, c.stream);
   return 0;
 }
 
 extern "C" int nb200_accumulate_clear(double* dst_device, double* src_device, size_t n) {
-  if (ensure_ready() != 0) return -1;
-  g.launches += launch_accumulate_clear(dst_device, src_device, n, g.stream);
+  CTX_OR_RETURN(c);
+  c.launches += launch_accumulate_clear(dst_device, src_device, n, c.stream);
   return 0;
 }
 
 extern "C" int nb200_accumulate_clear_async(double* dst_device, double* src_device, size_t n,
                                             void* cuda_stream) {
-  if (ensure_ready() != 0) return -1;
-  g.launches += launch_accumulate_clear(dst_device, src_device, n, (cudaStream_t)cuda_stream);
+  CTX_OR_RETURN(c);
+  c.launches += launch_accumulate_clear(dst_device, src_device, n, (cudaStream_t)cuda_stream);
   return 0;
 }
 
 extern "C" int nb200_bank_export(nb200_particle_soa* particles) {
-  if (ensure_ready() != 0) return -1;
+  CTX_OR_RETURN(c0);
+  (void)c0;
   Bank* bank = bank_of(particles);
-  if (!bank) {
-    set_error("nb200_bank_export: not a bank handle");
+  if (!bank || !single_shard(bank)) {
+    set_error("nb200_bank_export: not a (single-GPU) bank handle");
     return -3;
   }
-  if (!bank->has_export) {
-    soa_alloc(bank->exported, bank->n);
-    bank->has_export = true;
-    reinterpret_cast<BankHandle*>(particles)->view = as_public(bank->exported);
-  }
-  g.launches += launch_export_soa(bank->cur, bank->exported, bank->n, g.stream);
-  CU_TRY(cudaStreamSynchronize(g.stream));
+  if (int rc = refuse_if_pending(bank, "nb200_bank_export")) return rc;
+  Shard& sh = bank->shards[0];
+  DeviceGuard guard(sh.dev);
+  DeviceCtx& c = ctx_on(sh.dev);
+  ensure_export(c, sh);
+  if (!bank->mirror.present) set_views(bank, as_public(sh.exported));
+  c.launches += launch_export_soa(sh.cur, sh.exported, sh.n, c.stream);
+  CU_TRY(cudaStreamSynchronize(c.stream));
   return 0;
 }
 
 extern "C" int nb200_bank_download(nb200_particle_soa* particles, nb200_particle_soa* host) {
-  const int rc = nb200_bank_export(particles);
-  if (rc != 0) return rc;
+  CTX_OR_RETURN(c0);
+  (void)c0;
   Bank* bank = bank_of(particles);
-  const SoaView& s = bank->exported;
-  const size_t n = (size_t)bank->n;
-  const double* dd[] = {s.x, s.y, s.omega_x, s.omega_y, s.energy, s.weight, s.dt_to_census,
-                        s.mfp_to_collision};
-  double* hd[] = {host->x, host->y, host->omega_x, host->omega_y, host->energy, host->weight,
-                  host->dt_to_census, host->mfp_to_collision};
-  for (int k = 0; k < 8; ++k)
-    CU_TRY(cudaMemcpyAsync(hd[k], dd[k], sizeof(double) * n, cudaMemcpyDeviceToHost, g.stream));
-  const int* di[] = {s.cellx, s.celly, s.dead};
-  int* hi[] = {host->cellx, host->celly, host->dead};
-  for (int k = 0; k < 3; ++k)
-    CU_TRY(cudaMemcpyAsync(hi[k], di[k], sizeof(int) * n, cudaMemcpyDeviceToHost, g.stream));
-  CU_TRY(cudaStreamSynchronize(g.stream));
+  if (!bank || !host) {
+    set_error("nb200_bank_download: not a bank handle");
+    return -3;
+  }
+  if (int rc = refuse_if_pending(bank, "nb200_bank_download")) return rc;
+  download_to_host(bank, as_soa_view(*host));
   return 0;
 }
 
 extern "C" int nb200_bank_copy(nb200_particle_soa* dst, nb200_particle_soa* src) {
-  if (ensure_ready() != 0) return -1;
+  CTX_OR_RETURN(c0);
+  (void)c0;
   Bank* d = bank_of(dst);
   Bank* s = bank_of(src);
-  if (!d || !s || d->n != s->n) {
-    set_error("nb200_bank_copy: handles must be banks of the same size");
+  if (!d || !s || d->n != s->n || d->shards.size() != s->shards.size()) {
+    set_error("nb200_bank_copy: handles must be banks of the same size and sharding");
     return -3;
   }
-  const size_t n = (size_t)s->n;
-  CU_TRY(cudaMemcpyAsync(d->cur.pos, s->cur.pos, sizeof(double2) * n, cudaMemcpyDeviceToDevice, g.stream));
-  CU_TRY(cudaMemcpyAsync(d->cur.dir, s->cur.dir, sizeof(double2) * n, cudaMemcpyDeviceToDevice, g.stream));
-  CU_TRY(cudaMemcpyAsync(d->cur.ew, s->cur.ew, sizeof(double2) * n, cudaMemcpyDeviceToDevice, g.stream));
-  CU_TRY(cudaMemcpyAsync(d->cur.tm, s->cur.tm, sizeof(double2) * n, cudaMemcpyDeviceToDevice, g.stream));
-  CU_TRY(cudaMemcpyAsync(d->cur.meta, s->cur.meta, sizeof(int4) * n, cudaMemcpyDeviceToDevice, g.stream));
+  if (int rc = refuse_if_pending(d, "nb200_bank_copy")) return rc;
+  if (int rc = refuse_if_pending(s, "nb200_bank_copy")) return rc;
+  for (size_t si = 0; si < d->shards.size(); ++si) {
+    Shard& ds = d->shards[si];
+    Shard& ss = s->shards[si];
+    if (ds.dev != ss.dev || ds.n != ss.n) {
+      set_error("nb200_bank_copy: shard %zu differs in device or size", si);
+      return -3;
+    }
+    DeviceGuard guard(ds.dev);
+    DeviceCtx& c = ctx_on(ds.dev);
+    const size_t n = (size_t)ss.n;
+    CU_TRY(cudaMemcpyAsync(ds.cur.pos, ss.cur.pos, sizeof(double2) * n, cudaMemcpyDeviceToDevice, c.stream));
+    CU_TRY(cudaMemcpyAsync(ds.cur.dir, ss.cur.dir, sizeof(double2) * n, cudaMemcpyDeviceToDevice, c.stream));
+    CU_TRY(cudaMemcpyAsync(ds.cur.ew, ss.cur.ew, sizeof(double2) * n, cudaMemcpyDeviceToDevice, c.stream));
+    CU_TRY(cudaMemcpyAsync(ds.cur.tm, ss.cur.tm, sizeof(double2) * n, cudaMemcpyDeviceToDevice, c.stream));
+    CU_TRY(cudaMemcpyAsync(ds.cur.meta, ss.cur.meta, sizeof(int4) * n, cudaMemcpyDeviceToDevice, c.stream));
+    ds.pid0 = ss.pid0;
+    ds.n_upper = ss.n_upper;
+  }
   d->pid0 = s->pid0;
-  d->n_upper = s->n_upper;
   return 0;
 }
 
@@ -1111,16 +1810,97 @@ extern "C" int nb200_bank_size(nb200_particle_soa* particles) {
   return bank ? bank->n : -3;
 }
 
+extern "C" int nb200_bank_capacity(nb200_particle_soa* particles) {
+  Bank* bank = bank_of(particles);
+  if (!bank) return -3;
+  long long cap = 0;
+  for (const Shard& sh : bank->shards) cap += sh.capacity;
+  return (int)std::min<long long>(cap, INT_MAX);
+}
+
+extern "C" int nb200_bank_gpus(nb200_particle_soa* particles) {
+  Bank* bank = bank_of(particles);
+  return bank ? (int)bank->shards.size() : -3;
+}
+
+// Appends `count` particles (host SoA arrays) into the bank's head-room: they become
+// particles [n, n + count) in injection order, global index pid0 + n + i (single-GPU banks).
+extern "C" int nb200_bank_append(nb200_particle_soa* particles, const nb200_particle_soa* host,
+                                 int count) {
+  CTX_OR_RETURN(c0);
+  (void)c0;
+  Bank* bank = bank_of(particles);
+  if (!bank || !host || count < 0 || !single_shard(bank)) {
+    set_error("nb200_bank_append: not a (single-GPU) bank handle");
+    return -3;
+  }
+  if (int rc = refuse_if_pending(bank, "nb200_bank_append")) return rc;
+  Shard& sh = bank->shards[0];
+  if (bank->mirror.present) {
+    set_error("nb200_bank_append: banks with a host mirror cannot grow");
+    return -3;
+  }
+  if (sh.n + count > sh.capacity) {
+    set_error("nb200_bank_append: %d particles do not fit the head-room (%d of %d slots used; "
+              "option headroom_pct)", count, sh.n, sh.capacity);
+    return -5;
+  }
+  if (count == 0) return 0;
+  DeviceGuard guard(sh.dev);
+  DeviceCtx& c = ctx_on(sh.dev);
+  SoaView staging{};
+  soa_alloc(c, staging, count);
+  const SoaView h = as_soa_view(*host);
+  const double* hd[] = {h.x, h.y, h.omega_x, h.omega_y, h.energy, h.weight, h.dt_to_census,
+                        h.mfp_to_collision};
+  double* dd[] = {staging.x, staging.y, staging.omega_x, staging.omega_y, staging.energy,
+                  staging.weight, staging.dt_to_census, staging.mfp_to_collision};
+  for (int k = 0; k < 8; ++k)
+    CU_TRY(cudaMemcpyAsync(dd[k], hd[k], sizeof(double) * count, cudaMemcpyHostToDevice, c.stream));
+  const int* hi[] = {h.cellx, h.celly, h.dead};
+  int* di[] = {staging.cellx, staging.celly, staging.dead};
+  for (int k = 0; k < 3; ++k)
+    CU_TRY(cudaMemcpyAsync(di[k], hi[k], sizeof(int) * count, cudaMemcpyHostToDevice, c.stream));
+  // the new records go behind the last slot, with the next origins
+  BankView tail = sh.cur;
+  tail.pos += sh.n; tail.dir += sh.n; tail.ew += sh.n; tail.tm += sh.n; tail.meta += sh.n;
+  c.launches += launch_import_soa(tail, staging, count, sh.n, c.stream);
+  CU_TRY(cudaStreamSynchronize(c.stream));
+  soa_release(staging);
+  sh.n += count;
+  sh.n_upper = sh.n;  // the live prefix is unknown again: the next sort visits every slot
+  bank->n += count;
+  if (sh.has_export) {  // the plain view was sized for the old bank only if capacity == n
+    // (it is allocated with `capacity` slots, so nothing to do)
+  }
+  return 0;
+}
+
 extern "C" int nb200_bank_free(nb200_particle_soa* particles) {
   Bank* bank = bank_of(particles);
   if (!bank) return -3;
-  bank_release(bank->cur);
-  if (bank->has_alt) {
-    bank_release(bank->alt);
-    cudaFree(bank->keys);
+  finish_all(bank);
+  if (bank->group) {
+    group_flush(*bank->group);
+    group_free(bank->group);
   }
-  if (bank->has_export) soa_release(bank->exported);
-  BankHandle* h = reinterpret_cast<BankHandle*>(particles);
+  for (Shard& sh : bank->shards) {
+    DeviceGuard guard(sh.dev);
+    bank_release(sh.cur);
+    if (sh.has_alt) {
+      bank_release(sh.alt);
+      cudaFree(sh.keys);
+    }
+    if (sh.has_export) soa_release(sh.exported);
+  }
+  if (bank->mirror.present) {
+    nb200_particle_soa& a = bank->mirror.a;
+    void* p[] = {a.x, a.y, a.omega_x, a.omega_y, a.energy, a.weight, a.dt_to_census,
+                 a.mfp_to_collision, a.cellx, a.celly, a.dead};
+    for (void* q : p) cudaFreeHost(q);
+  }
+  if (g_last_deferred == bank) g_last_deferred = nullptr;
+  BankHeader* h = bank->header;
   h->magic = 0;
   delete bank;
   free(h);
@@ -1128,22 +1908,25 @@ extern "C" int nb200_bank_free(nb200_particle_soa* particles) {
 }
 
 extern "C" int nb200_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes) {
-  if (ensure_ready() != 0) return -1;
-  CU_TRY(cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, g.stream));
-  CU_TRY(cudaStreamSynchronize(g.stream));
+  CTX_OR_RETURN(c);
+  flush_groups_touching(dst_device, bytes);
+  CU_TRY(cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, c.stream));
+  CU_TRY(cudaStreamSynchronize(c.stream));
   return 0;
 }
 
 extern "C" int nb200_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes) {
-  if (ensure_ready() != 0) return -1;
-  CU_TRY(cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, g.stream));
-  CU_TRY(cudaStreamSynchronize(g.stream));
+  CTX_OR_RETURN(c);
+  flush_groups_touching(src_device, bytes);
+  CU_TRY(cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, c.stream));
+  CU_TRY(cudaStreamSynchronize(c.stream));
   return 0;
 }
 
 extern "C" int nb200_memcpy_h2d_async(void* dst_device, const void* src_host, size_t bytes,
                                       void* cuda_stream) {
-  if (ensure_ready() != 0) return -1;
+  CTX_OR_RETURN(c);
+  (void)c;
   CU_TRY(cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice,
                          (cudaStream_t)cuda_stream));
   return 0;
@@ -1151,80 +1934,262 @@ extern "C" int nb200_memcpy_h2d_async(void* dst_device, const void* src_host, si
 
 extern "C" int nb200_memcpy_d2h_async(void* dst_host, const void* src_device, size_t bytes,
                                       void* cuda_stream) {
-  if (ensure_ready() != 0) return -1;
+  CTX_OR_RETURN(c);
+  (void)c;
+  flush_groups_touching(src_device, bytes);
   CU_TRY(cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost,
                          (cudaStream_t)cuda_stream));
   return 0;
 }
 
 extern "C" int nb200_memset_d(void* dst_device, int value, size_t bytes) {
-  if (ensure_ready() != 0) return -1;
-  CU_TRY(cudaMemsetAsync(dst_device, value, bytes, g.stream));
+  CTX_OR_RETURN(c);
+  flush_groups_touching(dst_device, bytes);
+  CU_TRY(cudaMemsetAsync(dst_device, value, bytes, c.stream));
   return 0;
 }
 
 extern "C" int nb200_synchronize(void) {
-  if (ensure_ready() != 0) return -1;
-  CU_TRY(cudaStreamSynchronize(g.stream));
+  CTX_OR_RETURN(c);
+  CU_TRY(cudaStreamSynchronize(c.stream));
   return 0;
 }
 
 extern "C" int nb200_set_option(const char* name, int value) {
-  int* slot = nullptr;
-  if (strcmp(name, "print") == 0) slot = &g.opt_print;
-  else if (strcmp(name, "pipeline") == 0) slot = &g.opt_pipeline;
-  else if (strcmp(name, "fast_div") == 0) slot = &g.opt_fast_div;
-  else if (strcmp(name, "tile_shift") == 0) slot = &g.opt_tile_shift;
-  else if (strcmp(name, "length_bins") == 0) slot = &g.opt_length_bins;
-  else if (strcmp(name, "tally_prereduce") == 0) slot = &g.opt_tally_prereduce;
-  else if (strcmp(name, "l2_persist") == 0) slot = &g.opt_l2_persist;
-  else if (strcmp(name, "defer_finish") == 0) slot = &g.opt_defer_finish;
-  else if (strcmp(name, "device_inject") == 0) slot = &g.opt_device_inject;
-  else if (strcmp(name, "stage_overlap") == 0) slot = &g.opt_stage_overlap;
-  else if (strcmp(name, "history_smem_pad") == 0) slot = &g.opt_history_smem_pad;
-  if (!slot) {
+  read_environment();
+  const int i = option_index(name);
+  if (i < 0) {
     set_error("nb200_set_option: unknown option '%s'", name);
-    return -3;
+    return NB200_BAD_OPTION;
   }
-  const int prev = *slot;
-  *slot = value;
+  const OptionSpec& spec = kOptionSpecs[i];
+  if (value < spec.lo || value > spec.hi) {
+    set_error("nb200_set_option: %s=%d is outside [%d, %d]", name, value, spec.lo, spec.hi);
+    return NB200_BAD_OPTION;
+  }
+  const int prev = g_opt.*(spec.slot);
+  g_opt.*(spec.slot) = value;
+  return prev;
+}
+
+extern "C" int nb200_get_option(const char* name) {
+  read_environment();
+  const int i = option_index(name);
+  if (i < 0) {
+    set_error("nb200_get_option: unknown option '%s'", name);
+    return NB200_BAD_OPTION;
+  }
+  return g_opt.*(kOptionSpecs[i].slot);
+}
+
+extern "C" int nb200_bank_set_option(nb200_particle_soa* particles, const char* name, int value) {
+  Bank* bank = bank_of(particles);
+  const int i = option_index(name);
+  if (!bank || i < 0) {
+    set_error("nb200_bank_set_option: not a bank handle, or unknown option '%s'", name);
+    return NB200_BAD_OPTION;
+  }
+  const OptionSpec& spec = kOptionSpecs[i];
+  if (value < spec.lo || value > spec.hi) {
+    set_error("nb200_bank_set_option: %s=%d is outside [%d, %d]", name, value, spec.lo, spec.hi);
+    return NB200_BAD_OPTION;
+  }
+  const int prev = opt_of(bank, spec.slot);
+  for (auto& o : bank->overrides)
+    if (o.first == i) {
+      o.second = value;
+      return prev;
+    }
+  bank->overrides.push_back({i, value});
   return prev;
 }
 
 extern "C" int nb200_solve_finish(uint64_t* facet_events, uint64_t* collision_events) {
-  if (!g.pending_bank) {
+  if (!g_last_deferred || g_last_deferred->pending.empty()) {
     set_error("nb200_solve_finish: no timestep is pending");
     return -3;
   }
-  uint64_t f = 0, c = 0;
-  finish_step(&f, &c);
-  if (facet_events) *facet_events += f;
-  if (collision_events) *collision_events += c;
+  finish_oldest(g_last_deferred, facet_events, collision_events);
   return 0;
+}
+
+extern "C" int nb200_bank_solve_finish(nb200_particle_soa* particles, uint64_t* facet_events,
+                                       uint64_t* collision_events) {
+  Bank* bank = bank_of(particles);
+  if (!bank || bank->pending.empty()) {
+    set_error("nb200_bank_solve_finish: not a bank handle, or no timestep is pending");
+    return -3;
+  }
+  finish_oldest(bank, facet_events, collision_events);
+  return 0;
+}
+
+extern "C" int nb200_bank_pending(nb200_particle_soa* particles) {
+  Bank* bank = bank_of(particles);
+  return bank ? (int)bank->pending.size() : -3;
 }
 
 extern "C" int nb200_last_step_stats(uint64_t out[8]) {
-  for (int k = 0; k < 8; ++k) out[k] = g.last_stats[k];
+  for (int k = 0; k < 8; ++k) out[k] = g_last_stats[k];
   return 0;
 }
 
-extern "C" uint64_t nb200_kernel_launches(void) { return g.launches; }
+extern "C" uint64_t nb200_kernel_launches(void) {
+  uint64_t total = 0;
+  for (DeviceCtx* c : g_ctx)
+    if (c) total += c->launches;
+  return total;
+}
 
+// ----------------------------------------------------------------- sharded runs: tally --
+extern "C" int nb200_tally_sync(double* tally_device) {
+  CTX_OR_RETURN(c);
+  (void)c;
+  for (TallyGroup* g : g_groups)
+    if (!tally_device || g->target == tally_device) group_flush(*g);
+  return 0;
+}
+
+extern "C" int nb200_update_replicas(void) {
+  g_replica_generation++;
+  return 0;
+}
+
+// Multi-process sharding (one process per GPU): this process's member of the group, and the
+// blob its peers need to map it.
+extern "C" int nb200_mp_init(int nranks, int rank, size_t ncells, void* blob_out) {
+  CTX_OR_RETURN(c);
+  if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks || !ncells || !blob_out) {
+    set_error("nb200_mp_init: bad arguments (nranks=%d rank=%d ncells=%zu)", nranks, rank, ncells);
+    return -3;
+  }
+  if (g_mp) {
+    set_error("nb200_mp_init: a multi-process group already exists (nb200_mp_finalize first)");
+    return -3;
+  }
+  TallyGroup* g = new TallyGroup();
+  g->nranks = nranks;
+  g->ncells = ncells;
+  g->collective = g_opt.collective;
+  g->reduce_ctas = g_opt.reduce_ctas;
+  g->mp = true;
+  g->mp_rank = rank;
+  group_layout(*g);
+  group_alloc_member(*g, rank, c.device);
+  memset(blob_out, 0, NB200_MP_BLOB_BYTES);
+  char* blob = (char*)blob_out;
+  if (g->collective) {
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, g->m[rank].slab));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(blob, &h, 64);
+  } else if (rank == 0) {
+    std::string why;
+    const NcclApi* api = nccl_api(&why);
+    if (!api) {
+      set_error("nb200_mp_init: %s", why.c_str());
+      return -6;
+    }
+    NcclUniqueId id;
+    if (api->GetUniqueId(&id) != kNcclSuccess) {
+      set_error("nb200_mp_init: ncclGetUniqueId failed");
+      return -6;
+    }
+    memcpy(blob + 64, &id, 128);
+  }
+  g_mp = g;
+  return 0;
+}
+
+extern "C" int nb200_mp_connect(const void* blobs) {
+  CTX_OR_RETURN(c);
+  (void)c;
+  if (!g_mp || !blobs) {
+    set_error("nb200_mp_connect: nb200_mp_init has not been called");
+    return -3;
+  }
+  TallyGroup& g = *g_mp;
+  const char* all = (const char*)blobs;
+  if (g.collective) {
+    for (int r = 0; r < g.nranks; ++r) {
+      if (r == g.mp_rank) continue;
+      cudaIpcMemHandle_t h;
+      memcpy(&h, all + (size_t)r * NB200_MP_BLOB_BYTES, 64);
+      void* base = nullptr;
+      const cudaError_t err = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+      if (err != cudaSuccess) {
+        set_error("nb200_mp_connect: cannot map rank %d's tally slab over CUDA IPC: %s", r,
+                  cudaGetErrorString(err));
+        (void)cudaGetLastError();
+        return -7;
+      }
+      group_bind(g, g.m[r], (char*)base);
+      g.m[r].ipc_opened = true;
+    }
+  } else {
+    std::string why;
+    const NcclApi* api = nccl_api(&why);
+    if (!api) {
+      set_error("nb200_mp_connect: %s", why.c_str());
+      return -6;
+    }
+    NcclUniqueId id;
+    memcpy(&id, all + 64, 128);  // rank 0's blob carries the id
+    const int rc = api->CommInitRank(&g.m[g.mp_rank].comm, g.nranks, id, g.mp_rank);
+    if (rc != kNcclSuccess) {
+      set_error("nb200_mp_connect: ncclCommInitRank failed: %s", api->GetErrorString(rc));
+      return -6;
+    }
+  }
+  g_groups.push_back(g_mp);
+  return 0;
+}
+
+extern "C" int nb200_mp_finalize(void) {
+  if (!g_mp) return 0;
+  group_free(g_mp);
+  g_mp = nullptr;
+  return 0;
+}
+
+// ------------------------------------------------------------------------- microbench --
+extern "C" int nb200_microbench_red(int pattern, size_t footprint_bytes, int iters,
+                                    double* reductions_per_s) {
+  CTX_OR_RETURN(c);
+  size_t cells = 1;
+  while (cells * 2 * sizeof(double) <= footprint_bytes) cells *= 2;  // power of two
+  if (cells < 1024 || iters < 1 || !reductions_per_s) {
+    set_error("nb200_microbench_red: bad arguments");
+    return -3;
+  }
+  double* scratch = nullptr;
+  CU_TRY(cudaMalloc(&scratch, cells * sizeof(double)));
+  CU_TRY(cudaMemsetAsync(scratch, 0, cells * sizeof(double), c.stream));
+  double seconds = 0.0, reds = 0.0;
+  c.launches += launch_red_rate(scratch, cells, 4000, iters, pattern, c.ev_begin[0], c.ev_end[0],
+                                &seconds, &reds, c.stream);
+  cudaFree(scratch);
+  CU_TRY(cudaGetLastError());
+  *reductions_per_s = seconds > 0.0 ? reds / seconds : 0.0;
+  return 0;
+}
+
+// ---------------------------------------------------------------------- self-test hooks --
 extern "C" int nb200_selftest_rng_log(uint64_t pkey0, uint64_t master_key, uint64_t counter,
                                       int n, uint64_t* raw_host, double* unit_host,
                                       double* neglog_host) {
-  if (ensure_ready() != 0) return -1;
+  CTX_OR_RETURN(c);
   uint64_t* d_raw = nullptr;
   double *d_unit = nullptr, *d_nl = nullptr;
   CU_TRY(cudaMalloc(&d_raw, sizeof(uint64_t) * 2 * n));
   CU_TRY(cudaMalloc(&d_unit, sizeof(double) * 2 * n));
   CU_TRY(cudaMalloc(&d_nl, sizeof(double) * 2 * n));
-  g.launches += launch_selftest_rng_log(pkey0, master_key, counter, n, g.d_logt, d_raw, d_unit,
-                                        d_nl, g.stream);
-  CU_TRY(cudaMemcpyAsync(raw_host, d_raw, sizeof(uint64_t) * 2 * n, cudaMemcpyDeviceToHost, g.stream));
-  CU_TRY(cudaMemcpyAsync(unit_host, d_unit, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, g.stream));
-  CU_TRY(cudaMemcpyAsync(neglog_host, d_nl, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, g.stream));
-  CU_TRY(cudaStreamSynchronize(g.stream));
+  c.launches += launch_selftest_rng_log(pkey0, master_key, counter, n, c.d_logt, d_raw, d_unit,
+                                        d_nl, c.stream);
+  CU_TRY(cudaMemcpyAsync(raw_host, d_raw, sizeof(uint64_t) * 2 * n, cudaMemcpyDeviceToHost, c.stream));
+  CU_TRY(cudaMemcpyAsync(unit_host, d_unit, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, c.stream));
+  CU_TRY(cudaMemcpyAsync(neglog_host, d_nl, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, c.stream));
+  CU_TRY(cudaStreamSynchronize(c.stream));
   cudaFree(d_raw);
   cudaFree(d_unit);
   cudaFree(d_nl);
@@ -1232,14 +2197,14 @@ extern "C" int nb200_selftest_rng_log(uint64_t pkey0, uint64_t master_key, uint6
 }
 
 extern "C" int nb200_selftest_log(const double* x_host, double* y_host, int n) {
-  if (ensure_ready() != 0) return -1;
+  CTX_OR_RETURN(c);
   double *d_x = nullptr, *d_y = nullptr;
   CU_TRY(cudaMalloc(&d_x, sizeof(double) * n));
   CU_TRY(cudaMalloc(&d_y, sizeof(double) * n));
-  CU_TRY(cudaMemcpyAsync(d_x, x_host, sizeof(double) * n, cudaMemcpyHostToDevice, g.stream));
-  g.launches += launch_selftest_log(d_x, d_y, n, g.d_logt, g.stream);
-  CU_TRY(cudaMemcpyAsync(y_host, d_y, sizeof(double) * n, cudaMemcpyDeviceToHost, g.stream));
-  CU_TRY(cudaStreamSynchronize(g.stream));
+  CU_TRY(cudaMemcpyAsync(d_x, x_host, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+  c.launches += launch_selftest_log(d_x, d_y, n, c.d_logt, c.stream);
+  CU_TRY(cudaMemcpyAsync(y_host, d_y, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+  CU_TRY(cudaStreamSynchronize(c.stream));
   cudaFree(d_x);
   cudaFree(d_y);
   return 0;
@@ -1248,7 +2213,7 @@ extern "C" int nb200_selftest_log(const double* x_host, double* y_host, int n) {
 extern "C" int nb200_selftest_cs(const double* keys_host, const double* values_host,
                                  int nentries, const double* energies_host, int n,
                                  int* index_host, double* value_host) {
-  if (ensure_ready() != 0) return -1;
+  CTX_OR_RETURN(c);
   double *d_k = nullptr, *d_v = nullptr, *d_e = nullptr, *d_o = nullptr;
   int* d_i = nullptr;
   CU_TRY(cudaMalloc(&d_k, sizeof(double) * nentries));
@@ -1256,23 +2221,25 @@ extern "C" int nb200_selftest_cs(const double* keys_host, const double* values_h
   CU_TRY(cudaMalloc(&d_e, sizeof(double) * n));
   CU_TRY(cudaMalloc(&d_o, sizeof(double) * n));
   CU_TRY(cudaMalloc(&d_i, sizeof(int) * n));
-  CU_TRY(cudaMemcpyAsync(d_k, keys_host, sizeof(double) * nentries, cudaMemcpyHostToDevice, g.stream));
-  CU_TRY(cudaMemcpyAsync(d_v, values_host, sizeof(double) * nentries, cudaMemcpyHostToDevice, g.stream));
-  CU_TRY(cudaMemcpyAsync(d_e, energies_host, sizeof(double) * n, cudaMemcpyHostToDevice, g.stream));
+  CU_TRY(cudaMemcpyAsync(d_k, keys_host, sizeof(double) * nentries, cudaMemcpyHostToDevice, c.stream));
+  CU_TRY(cudaMemcpyAsync(d_v, values_host, sizeof(double) * nentries, cudaMemcpyHostToDevice, c.stream));
+  CU_TRY(cudaMemcpyAsync(d_e, energies_host, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
   // stage the table exactly as a timestep does, then run both lookups side by side
-  const CsParams par = cs_params_from_host(keys_host, nentries);
+  const CsParams par = nentries >= 2
+                           ? cs_params_from_ends(keys_host[0], keys_host[nentries - 1], nentries)
+                           : CsParams();
   double2* d_kv = nullptr;
   int* d_bk = nullptr;
   CU_TRY(cudaMalloc(&d_kv, sizeof(double2) * nentries));
   CU_TRY(cudaMalloc(&d_bk, sizeof(int) * (par.nb + 1)));
-  CU_TRY(cudaMemsetAsync(g.d_totals, 0, sizeof(unsigned long long) * kTotCount, g.stream));
-  g.launches += launch_stage_cs(d_k, d_v, nentries, d_kv, d_bk, par.bits0, par.shift, par.nb,
-                                nullptr, g.d_totals, g.stream);
+  CU_TRY(cudaMemsetAsync(c.d_totals, 0, sizeof(unsigned long long) * kTotCount, c.stream));
+  c.launches += launch_stage_cs(d_k, d_v, nentries, d_kv, d_bk, par.bits0, par.shift, par.nb,
+                                nullptr, c.d_totals, c.stream);
   const CsStage staged{d_kv, d_bk, par.bits0, par.shift, par.nb, nentries};
-  g.launches += launch_selftest_cs(d_k, d_v, nentries, staged, d_e, n, d_i, d_o, g.stream);
-  CU_TRY(cudaMemcpyAsync(index_host, d_i, sizeof(int) * n, cudaMemcpyDeviceToHost, g.stream));
-  CU_TRY(cudaMemcpyAsync(value_host, d_o, sizeof(double) * n, cudaMemcpyDeviceToHost, g.stream));
-  CU_TRY(cudaStreamSynchronize(g.stream));
+  c.launches += launch_selftest_cs(d_k, d_v, nentries, staged, d_e, n, d_i, d_o, c.stream);
+  CU_TRY(cudaMemcpyAsync(index_host, d_i, sizeof(int) * n, cudaMemcpyDeviceToHost, c.stream));
+  CU_TRY(cudaMemcpyAsync(value_host, d_o, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+  CU_TRY(cudaStreamSynchronize(c.stream));
   cudaFree(d_k); cudaFree(d_v); cudaFree(d_e); cudaFree(d_o); cudaFree(d_i);
   cudaFree(d_kv); cudaFree(d_bk);
   return 0;
@@ -1280,32 +2247,32 @@ extern "C" int nb200_selftest_cs(const double* keys_host, const double* values_h
 
 extern "C" int nb200_selftest_div(const double* a_host, const double* b_host, int n,
                                   double* fast_host, double* ieee_host) {
-  if (ensure_ready() != 0) return -1;
+  CTX_OR_RETURN(c);
   double* d[4] = {nullptr, nullptr, nullptr, nullptr};
   for (auto& p : d) CU_TRY(cudaMalloc(&p, sizeof(double) * n));
-  CU_TRY(cudaMemcpyAsync(d[0], a_host, sizeof(double) * n, cudaMemcpyHostToDevice, g.stream));
-  CU_TRY(cudaMemcpyAsync(d[1], b_host, sizeof(double) * n, cudaMemcpyHostToDevice, g.stream));
-  g.launches += launch_selftest_div(d[0], d[1], d[2], d[3], n, g.stream);
-  CU_TRY(cudaMemcpyAsync(fast_host, d[2], sizeof(double) * n, cudaMemcpyDeviceToHost, g.stream));
-  CU_TRY(cudaMemcpyAsync(ieee_host, d[3], sizeof(double) * n, cudaMemcpyDeviceToHost, g.stream));
-  CU_TRY(cudaStreamSynchronize(g.stream));
+  CU_TRY(cudaMemcpyAsync(d[0], a_host, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+  CU_TRY(cudaMemcpyAsync(d[1], b_host, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+  c.launches += launch_selftest_div(d[0], d[1], d[2], d[3], n, c.stream);
+  CU_TRY(cudaMemcpyAsync(fast_host, d[2], sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+  CU_TRY(cudaMemcpyAsync(ieee_host, d[3], sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+  CU_TRY(cudaStreamSynchronize(c.stream));
   for (auto& p : d) cudaFree(p);
   return 0;
 }
 
 extern "C" int nb200_selftest_fastmath(const double* a_host, const double* b_host, int n,
                                        double* out_host) {
-  if (ensure_ready() != 0) return -1;
+  CTX_OR_RETURN(c);
   double *d_a = nullptr, *d_b = nullptr, *d_o = nullptr;
   CU_TRY(cudaMalloc(&d_a, sizeof(double) * n));
   CU_TRY(cudaMalloc(&d_b, sizeof(double) * n));
   CU_TRY(cudaMalloc(&d_o, sizeof(double) * 6 * (size_t)n));
-  CU_TRY(cudaMemcpyAsync(d_a, a_host, sizeof(double) * n, cudaMemcpyHostToDevice, g.stream));
-  CU_TRY(cudaMemcpyAsync(d_b, b_host, sizeof(double) * n, cudaMemcpyHostToDevice, g.stream));
-  g.launches += launch_selftest_fastmath(d_a, d_b, d_o, n, g.stream);
+  CU_TRY(cudaMemcpyAsync(d_a, a_host, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+  CU_TRY(cudaMemcpyAsync(d_b, b_host, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+  c.launches += launch_selftest_fastmath(d_a, d_b, d_o, n, c.stream);
   CU_TRY(cudaMemcpyAsync(out_host, d_o, sizeof(double) * 6 * (size_t)n, cudaMemcpyDeviceToHost,
-                         g.stream));
-  CU_TRY(cudaStreamSynchronize(g.stream));
+                         c.stream));
+  CU_TRY(cudaStreamSynchronize(c.stream));
   cudaFree(d_a);
   cudaFree(d_b);
   cudaFree(d_o);
@@ -1354,14 +2321,14 @@ extern "C" long long nb200_selftest_host_sincos(const double* x, long long n, do
 // sin and cos of n host arguments, evaluated on the device.
 extern "C" int nb200_selftest_sincos(const double* x_host, double* s_host, double* c_host,
                                      int n) {
-  if (ensure_ready() != 0) return -1;
+  CTX_OR_RETURN(c);
   double *d_x = nullptr, *d_s = nullptr, *d_c = nullptr;
   CU_TRY(cudaMalloc(&d_x, sizeof(double) * n));
   CU_TRY(cudaMalloc(&d_s, sizeof(double) * n));
   CU_TRY(cudaMalloc(&d_c, sizeof(double) * n));
   CU_TRY(cudaMemcpy(d_x, x_host, sizeof(double) * n, cudaMemcpyHostToDevice));
-  g.launches += launch_selftest_sincos(d_x, d_s, d_c, n, g.d_sct, g.stream);
-  CU_TRY(cudaStreamSynchronize(g.stream));
+  c.launches += launch_selftest_sincos(d_x, d_s, d_c, n, c.d_sct, c.stream);
+  CU_TRY(cudaStreamSynchronize(c.stream));
   CU_TRY(cudaMemcpy(s_host, d_s, sizeof(double) * n, cudaMemcpyDeviceToHost));
   CU_TRY(cudaMemcpy(c_host, d_c, sizeof(double) * n, cudaMemcpyDeviceToHost));
   cudaFree(d_x);
@@ -1369,4 +2336,3 @@ extern "C" int nb200_selftest_sincos(const double* x_host, double* s_host, doubl
   cudaFree(d_c);
   return 0;
 }
-

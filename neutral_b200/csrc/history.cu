@@ -91,7 +91,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
     double dtc = tm.x, mfp = tm.y;
     int cx = m.x, cy = m.y;
 #define NB_CELL (cy * a.nx + cx)  // tally / density index of the current cell
-    unsigned flags = 0;
+    unsigned flags = same_grid(a) ? kFlagSameGrid : 0u;
     PARKED(e) = ew.x;
     PARKED(edep) = 0.0;
     PARKED(origin) = m.w;
@@ -285,7 +285,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
           mfp = neglog / PARKED(Sig_s);
         } else {
           bool done = false;
-          if (kFastDiv && a.same_keys) {
+          if (kFastDiv && (flags & kFlagSameGrid)) {
             // The whole scatter as one basic block (nb_history.cuh). It writes the state in
             // place; what the plain code below would need again if an operand turns out to be
             // outside the block's range is parked in the two slots this branch no longer

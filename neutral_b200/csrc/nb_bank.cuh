@@ -45,8 +45,12 @@ struct SoaView {
 // Step totals, one 64-bit counter each (device memory, zeroed by the host per step).
 // kTotFault is raised by the staging kernels when what they find on the device contradicts
 // what the host assumed (see stage.cu); the host turns it into a fatal error.
-enum { kTotFacets = 0, kTotCollisions, kTotProcessed, kTotCensus, kTotDeaths, kTotFault = 7,
-       kTotCount = 8 };
+// kTotGridsDiffer counts the grid points at which the two cross-section tables' energy grids
+// differ (stage.cu): whether "one search serves both tables" holds is decided where the data
+// is, every timestep, never from a host-side cache of what some pointer once held.
+// kTotGroupFault: a bounded wait of the tally collective expired (nb_group.cuh).
+enum { kTotFacets = 0, kTotCollisions, kTotProcessed, kTotCensus, kTotDeaths,
+       kTotGroupFault = 5, kTotGridsDiffer = 6, kTotFault = 7, kTotCount = 8 };
 
 // Staged copy of one reference CrossSection (neutral_data.h:38-43), rebuilt from the caller's
 // device arrays at the start of every timestep (stage.cu):
@@ -100,7 +104,9 @@ struct StepArgs {
   const double* a_keys;
   const double* a_vals;
   int s_n, a_n;
-  int same_keys;  // both tables share one energy grid (bitwise): one search serves both
+  // Both tables have the same number of grid points: they MAY share one energy grid (then one
+  // search serves both). Whether they do is totals[kTotGridsDiffer] == 0 - see same_grid().
+  int same_keys;
   double* tally;
   // Per-particle cumulative event counters indexed by origin (the interface's three
   // uint64[nparticles] scratch arrays, neutral_interface.h:19); may be null.

@@ -27,11 +27,18 @@ __device__ __forceinline__ double cs_interp(const double* __restrict__ keys,
   return v0 + ((e - k0) / (k1 - k0)) * (v1 - v0);
 }
 
+// The two tables share one energy grid, bit for bit: equal lengths (host) and no differing
+// grid point found by this timestep's staging kernel (device). The counter is written before
+// any kernel that asks and never while one runs.
+__device__ __forceinline__ bool same_grid(const StepArgs& a) {
+  return a.same_keys && a.totals[kTotGridsDiffer] == 0ull;
+}
+
 __device__ __forceinline__ void cs_lookup_pair(const StepArgs& a, double e, double& sig_s,
                                                double& sig_a) {
   const int is = cs_bracket(a.s_keys, a.s_n, e);
   sig_s = cs_interp(a.s_keys, a.s_vals, is, e);
-  const int ia = a.same_keys ? is : cs_bracket(a.a_keys, a.a_n, e);
+  const int ia = same_grid(a) ? is : cs_bracket(a.a_keys, a.a_n, e);
   sig_a = cs_interp(a.a_keys, a.a_vals, ia, e);
 }
 
@@ -58,13 +65,13 @@ __device__ __forceinline__ int cs_bracket_staged(const CsStage& c, double e) {
   return lo;
 }
 
-__device__ __forceinline__ void cs_lookup_pair_staged(const StepArgs& a, double e,
+__device__ __forceinline__ void cs_lookup_pair_staged(const StepArgs& a, double e, bool same,
                                                       double& sig_s, double& sig_a) {
   const int is = cs_bracket_staged(a.cs_s, e);
   const double2 s0 = __ldg(a.cs_s.kv + is), s1 = __ldg(a.cs_s.kv + is + 1);
   const double frac = (e - s0.x) / (s1.x - s0.x);
   sig_s = s0.y + frac * (s1.y - s0.y);
-  if (a.same_keys) {
+  if (same) {
     // identical grids: the interval and the interpolation weight are the same bits
     const double va0 = __ldg(&a.cs_a.kv[is].y), va1 = __ldg(&a.cs_a.kv[is + 1].y);
     sig_a = va0 + frac * (va1 - va0);

@@ -30,6 +30,7 @@ enum : unsigned {
   kFlagCoarseMixed = 4u,  // the current coarse tile is not uniform: consult the fine map
   kFlagFineMixed = 8u,    // nor is the current 16x16 tile: densities come from the mesh
   kFlagAnyMixed = kFlagCoarseMixed | kFlagFineMixed,
+  kFlagSameGrid = 2u,     // both tables share one energy grid (same_grid(), read once per step)
   kFlagPending = 16u,     // collisions deposited energy that no tally flush has taken yet
   kFlagDead = 32u,
 };
@@ -61,7 +62,7 @@ __device__ __forceinline__ bool finite_nonzero(double v) {
 __device__ __forceinline__ void derive(const StepArgs& a, double e, double nd, Derived& d,
                                        double& Sig_s, double& p_absorb, unsigned& flags) {
   double sig_s, sig_a;
-  cs_lookup_pair_staged(a, e, sig_s, sig_a);
+  cs_lookup_pair_staged(a, e, (flags & kFlagSameGrid) != 0u, sig_s, sig_a);
   const double sig_t = sig_s + sig_a;
   d.stb = sig_t * kBarns;
   const double S_s = macroscopic(nd, sig_s);

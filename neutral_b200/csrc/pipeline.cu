@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) k_begin_step(const StepArgs a, const Sort
       const int cx = m.x, cy = m.y;
       const double rho = __ldg(a.density + (size_t)cy * a.nx + cx);
       double sig_s, sig_a;
-      cs_lookup_pair_staged(a, e, sig_s, sig_a);
+      cs_lookup_pair_staged(a, e, same_grid(a), sig_s, sig_a);
       const double nd = number_density(rho);
       const double Sig_s = macroscopic(nd, sig_s);
       const double Sig_a = macroscopic(nd, sig_a);

@@ -47,9 +47,11 @@ __global__ void __launch_bounds__(256) k_stage_cs(const double* __restrict__ key
     // the grid must be strictly increasing (the reference's search assumes it,
     // omp3/neutral.c:506-511) ...
     bool fault = i > 0 && !(keys[i - 1] < k);
-    // ... and the host claimed both tables share one energy grid: verify it where the data is
-    if (twin_keys && double_to_bits(twin_keys[i]) != double_to_bits(k)) fault = true;
     if (fault) atomicAdd(totals + kTotFault, 1ull);
+    // ... and does the other table (same length) share this energy grid, bit for bit? Decided
+    // here, where the data is, every timestep (same_grid() in nb_device.cuh reads the count).
+    if (twin_keys && double_to_bits(twin_keys[i]) != double_to_bits(k))
+      atomicAdd(totals + kTotGridsDiffer, 1ull);
   }
   if (i <= nb) {
     int lo = 0, hi = n;  // first index whose bucket id is >= i
@@ -119,6 +121,15 @@ __global__ void __launch_bounds__(256) k_stage_edges(const double* __restrict__ 
   }
 }
 
+// The same verdict for the direct kernel, which reads the caller's tables unstaged.
+__global__ void __launch_bounds__(256) k_compare_grids(const double* __restrict__ a,
+                                                       const double* __restrict__ b, int n,
+                                                       unsigned long long* totals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && double_to_bits(a[i]) != double_to_bits(b[i]))
+    atomicAdd(totals + kTotGridsDiffer, 1ull);
+}
+
 static inline int blocks_for(size_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
 int launch_stage_cs(const double* keys, const double* vals, int n, double2* kv, int* bucket,
@@ -127,6 +138,13 @@ int launch_stage_cs(const double* keys, const double* vals, int n, double2* kv, 
   if (n <= 0) return 0;
   k_stage_cs<<<blocks_for((size_t)(n > nb + 1 ? n : nb + 1), 256), 256, 0, st>>>(keys, vals, n, kv, bucket, bits0, shift, nb,
                                                  twin_keys, totals);
+  return 1;
+}
+
+int launch_compare_grids(const double* a, const double* b, int n, unsigned long long* totals,
+                         cudaStream_t st) {
+  if (n <= 0) return 0;
+  k_compare_grids<<<blocks_for((size_t)n, 256), 256, 0, st>>>(a, b, n, totals);
   return 1;
 }
 

@@ -26,6 +26,8 @@ int launch_history(const StepArgs& a, const unsigned* n_live, int n_upper, bool 
 int launch_stage_cs(const double* keys, const double* vals, int n, double2* kv, int* bucket,
                     unsigned long long bits0, int shift, int nb, const double* twin_keys,
                     unsigned long long* totals, cudaStream_t st);
+int launch_compare_grids(const double* a, const double* b, int n, unsigned long long* totals,
+                         cudaStream_t st);
 // fine/coarse must hold tile_counts(nx, ny) doubles; *map receives the views.
 int launch_stage_tiles(const double* density, int nx, int ny, double* fine, double* coarse,
                        TileMap* map, cudaStream_t st);

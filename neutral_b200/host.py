@@ -51,7 +51,15 @@ EXPORTED_SYMBOLS = [
     "nb200_selftest_log", "nb200_selftest_div", "nb200_selftest_fastmath", "nb200_selftest_cs", "nb200_host_threefry2x64_20",
     "nb200_host_log", "nb200_selftest_sincos", "nb200_host_sin", "nb200_host_cos",
     "nb200_host_sincos", "nb200_selftest_host_sincos",
+    "nb200_bank_capacity", "nb200_bank_gpus", "nb200_bank_append", "nb200_get_option",
+    "nb200_bank_set_option", "nb200_bank_solve_finish", "nb200_bank_pending", "nb200_mp_init",
+    "nb200_mp_connect", "nb200_mp_finalize", "nb200_tally_sync", "nb200_update_replicas",
+    "nb200_microbench_red",
 ]
+
+#: include/neutral_b200.h
+NB200_BAD_OPTION = -2**31
+NB200_MP_BLOB_BYTES = 256
 
 _SOLVE_ARGS = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int,
                C.c_double, C.c_int, _ip, _ip, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -111,6 +119,17 @@ def load_library(build: bool = False) -> C.CDLL:
     L.nb200_bank_import.argtypes = [_soa_p]
     L.nb200_memset_d.argtypes = [C.c_void_p, C.c_int, C.c_size_t]
     L.nb200_set_option.argtypes = [C.c_char_p, C.c_int]
+    L.nb200_get_option.argtypes = [C.c_char_p]
+    L.nb200_bank_set_option.argtypes = [_soa_p, C.c_char_p, C.c_int]
+    L.nb200_bank_solve_finish.argtypes = [_soa_p, _u64p, _u64p]
+    L.nb200_bank_pending.argtypes = [_soa_p]
+    L.nb200_bank_capacity.argtypes = [_soa_p]
+    L.nb200_bank_gpus.argtypes = [_soa_p]
+    L.nb200_bank_append.argtypes = [_soa_p, _soa_p, C.c_int]
+    L.nb200_mp_init.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_void_p]
+    L.nb200_mp_connect.argtypes = [C.c_void_p]
+    L.nb200_tally_sync.argtypes = [C.c_void_p]
+    L.nb200_microbench_red.argtypes = [C.c_int, C.c_size_t, C.c_int, _dp]
     L.nb200_last_step_stats.argtypes = [_u64p]
     L.nb200_solve_finish.argtypes = [_u64p, _u64p]
     L.nb200_kernel_launches.restype = C.c_uint64
@@ -216,13 +235,16 @@ class Simulation:
     """
 
     def __init__(self, problem: Problem, rank: int = 0, nranks: int = 1,
-                 per_particle_counters: bool = True, quiet: bool = True):
+                 per_particle_counters: bool = True, quiet: bool = True, ngpus: int = 1):
         self.lib = load_library()
         require_device()
         self.problem = problem
         d = problem.deck
         self.pid0, self.count = shard_range(d.nparticles, rank, nranks)
         self.rank, self.nranks = rank, nranks
+        #: GPUs of THIS process the bank is sharded over (option "ngpus"): the library drives
+        #: them all behind the same solve_transport_2d call and combines the tally itself
+        self.ngpus = ngpus
         if quiet:
             self.lib.nb200_set_option(b"print", 0)
         self.density = DeviceArray.from_host(problem.density.ravel())
@@ -249,10 +271,12 @@ class Simulation:
         if self.bank is not None:
             self.lib.nb200_bank_free(self.bank)
         self.lib.nb200_set_shard(self.pid0, self.count if self.nranks > 1 else -1)
+        prev = self.lib.nb200_set_option(b"ngpus", self.ngpus)
         out = _soa_p()
         self.bank_bytes = self.lib.inject_particles(
             d.nparticles, d.nx, d.nx, d.ny, 0, s.left, s.bottom, s.width, s.height, 0, 0,
             d.dt, self.edgex.ptr, self.edgey.ptr, d.initial_energy, C.byref(out))
+        self.lib.nb200_set_option(b"ngpus", prev)
         self.lib.nb200_set_shard(0, -1)
         self.bank = out
         return self.bank_bytes
@@ -264,8 +288,10 @@ class Simulation:
             self.lib.nb200_bank_free(self.bank)
         st = host.as_struct()
         out = _soa_p()
+        prev = self.lib.nb200_set_option(b"ngpus", self.ngpus)
         _check(self.lib.nb200_bank_create(C.byref(st), self.count, self.pid0, C.byref(out)),
                "bank_create")
+        self.lib.nb200_set_option(b"ngpus", prev)
         self.bank = out
 
     def bank_to_host(self) -> HostBank:
@@ -281,8 +307,7 @@ class Simulation:
         ``defer=True`` returns as soon as the timestep is enqueued (library option
         ``defer_finish``); :meth:`step_finish` then waits for it and returns the counts."""
         d = self.problem.deck
-        if defer:
-            self.lib.nb200_set_option(b"defer_finish", 1)
+        self.lib.nb200_bank_set_option(self.bank, b"defer_finish", 1 if defer else 0)
         nlocal = C.c_int(self.count)
         facets, colls = C.c_uint64(0), C.c_uint64(0)
         ctr = [c.ptr for c in self.counters] if self.counters else [None] * 3
@@ -299,8 +324,8 @@ class Simulation:
     def step_finish(self) -> StepResult:
         """Completes a ``step(..., defer=True)``: waits for the timestep and returns its counts."""
         facets, colls = C.c_uint64(0), C.c_uint64(0)
-        _check(self.lib.nb200_solve_finish(C.byref(facets), C.byref(colls)), "solve_finish")
-        self.lib.nb200_set_option(b"defer_finish", 0)
+        _check(self.lib.nb200_bank_solve_finish(self.bank, C.byref(facets), C.byref(colls)),
+               "solve_finish")
         return self._result(facets.value, colls.value)
 
     def _result(self, facets: int, colls: int) -> StepResult:
@@ -313,6 +338,32 @@ class Simulation:
     def run(self, iterations: Optional[int] = None) -> List[StepResult]:
         n = self.problem.deck.iterations if iterations is None else iterations
         return [self.step(tt) for tt in range(1, n + 1)]
+
+    def run_pipelined(self, iterations: Optional[int] = None, first_tt: int = 1,
+                      depth: int = 3) -> List[StepResult]:
+        """The same timesteps without a host round trip between them: up to ``depth`` steps
+        are enqueued (``defer_finish``) before the oldest is collected, so the GPU goes from
+        one timestep's history kernel straight into the next one's sort. Results are those of
+        :meth:`run` (the steps execute in stream order either way)."""
+        n = self.problem.deck.iterations if iterations is None else iterations
+        out: List[StepResult] = []
+        inflight = 0
+        for tt in range(first_tt, first_tt + n):
+            self.step(tt, defer=True)
+            inflight += 1
+            if inflight >= depth:
+                out.append(self.step_finish())
+                inflight -= 1
+        while inflight:
+            out.append(self.step_finish())
+            inflight -= 1
+        self.lib.nb200_bank_set_option(self.bank, b"defer_finish", 0)
+        return out
+
+    def tally_sync(self) -> None:
+        """Brings ``self.tally`` up to date in a sharded run (a collective in a multi-process
+        group: every rank calls it)."""
+        _check(self.lib.nb200_tally_sync(self.tally.ptr), "tally_sync")
 
     # -- results ------------------------------------------------------------------------
     def tally_to_host(self) -> np.ndarray:

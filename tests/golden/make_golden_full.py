@@ -5,7 +5,12 @@ BASELINE.json decks at FULL size (4000 x 4000 mesh, 1e6 / 1e7 particles).
 Run in the build container, where /root/reference exists (oracle/Makefile compiles
 omp3/neutral.c in place into oracle/_ref/libneutral_omp3.so):
 
-    python tests/golden/make_golden_full.py [deck ...]        # ~10 CPU-minutes on 8 cores
+    python tests/golden/make_golden_full.py [deck[@nparticles] ...]   # ~10 CPU-minutes on 8 cores
+
+``deck@nparticles`` records the same deck with another particle count under that key: the
+weak-scaled banks bench.py transports on N GPUs (csp@2000000, csp@4000000, csp@8000000, the
+same for split) and the scaled-up split deck of BASELINE.json (split@100000000, ~40 minutes
+and 24 GB of host memory on 8 cores).
 
 Per deck it records, straight from the reference library:
   * per-timestep (facets, collisions)                                   [exact]
@@ -51,7 +56,8 @@ def main():
     result = json.load(open(OUT)) if os.path.exists(OUT) else {}
     devnull = os.open(os.devnull, os.O_WRONLY)
     for name in decks:
-        prob = build_problem(name)
+        base, _, count = name.partition("@")
+        prob = build_problem(base, nparticles=int(count)) if count else build_problem(base)
         d = prob.deck
         t0 = time.time()
         aos = ref.inject(prob)

@@ -11,7 +11,7 @@ import pytest
 from conftest import SMALL_DECKS
 from neutral_b200.bank import ALL_FIELDS, HostBank
 from neutral_b200.decks import build_problem
-from neutral_b200.host import Simulation, solve_transport_2d_host
+from neutral_b200.host import NB200_BAD_OPTION, Simulation, solve_transport_2d_host
 
 pytestmark = pytest.mark.gpu
 
@@ -48,7 +48,7 @@ def mode(request, gpu_lib):
     """Every kernel configuration must meet the same parity bar."""
     opts = MODES[request.param]
     for k, v in opts.items():
-        assert gpu_lib.nb200_set_option(k.encode(), v) >= -1
+        assert gpu_lib.nb200_set_option(k.encode(), v) != NB200_BAD_OPTION
     yield request.param
     for k, v in DEFAULTS.items():
         gpu_lib.nb200_set_option(k.encode(), v)

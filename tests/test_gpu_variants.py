@@ -4,7 +4,7 @@ per-particle and aggregate event counts, tally within 1e-10 relative per cell.""
 import numpy as np
 import pytest
 
-from neutral_b200.host import Simulation
+from neutral_b200.host import NB200_BAD_OPTION, Simulation
 from test_gpu_parity import DEFAULTS, MODES, tally_close
 from variants import VARIANTS
 
@@ -17,7 +17,7 @@ CONFIGS = ["pipeline", "pipeline-ieee-div", "direct"]
 @pytest.mark.parametrize("name", list(VARIANTS))
 def test_variant_matches_oracle_every_step(gpu_lib, port, name, config):
     for k, v in MODES[config].items():
-        assert gpu_lib.nb200_set_option(k.encode(), v) >= -1
+        assert gpu_lib.nb200_set_option(k.encode(), v) != NB200_BAD_OPTION
     try:
         prob = VARIANTS[name]()
         d = prob.deck
