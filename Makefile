@@ -5,7 +5,8 @@
 # own omp3 set the same way (that is the oracle/baseline build, see oracle/Makefile).
 #
 # Knobs mirror the reference Makefile:2-6,45-51: KERNELS, COMPILER (GCC only here), DEBUG,
-# OPTIONS. The absent `arch` parent project is served by archlite/ (SURVEY.md appendix A).
+# OPTIONS; NGPUS and DECK belong to the `run` target (`make run DECK=split NGPUS=8` shards the
+# bank over 8 GPUs of the box: the library reads NB200_NGPUS, the driver is unchanged). The absent `arch` parent project is served by archlite/ (SURVEY.md appendix A).
 # Outputs land in build/ (git-ignored; it travels to the GPU box through gpurun):
 #   build/run/neutral/neutral.$(KERNELS)   run it from build/run/neutral, like the reference:
 #       cd build/run/neutral && ./neutral.b200 problems/csp.params
@@ -30,8 +31,14 @@ endif
 INC      := -I$(SHIM)/a -I$(SHIM)/a/b -I$(SHIM)
 B200LIB  := $(ROOT)neutral_b200/libneutral_b200.so
 
-.PHONY: neutral lib clean rundir
+NGPUS    ?= 1
+DECK     ?= csp
+
+.PHONY: neutral lib clean rundir run
 neutral: $(RUN)/neutral.$(KERNELS)
+
+run: neutral
+	cd $(RUN) && NB200_NGPUS=$(NGPUS) ./neutral.$(KERNELS) problems/$(DECK).params
 
 lib $(B200LIB):
 	python -m neutral_b200.build

@@ -222,16 +222,42 @@ double reduce_all_sum(double local_val) { return local_val; }
 double reduce_all_min(double local_val) { return local_val; }
 double reduce_all_max(double local_val) { return local_val; }
 
+/* VisIt dump of one cell-centred field (main.c:129-139,169-200) as a Brick-of-Values pair,
+ * which VisIt opens natively: <name>.bov (text header) + <name>.dat (nx*ny doubles, row
+ * major). The field may be kernel-set (device) memory or the driver's own host buffer: it is
+ * staged through the allocation layer's copy_buffer either way. Single rank, no padding -
+ * the only configuration main.c produces (main.c:34,42-43). */
 void write_all_ranks_to_visit(const int global_nx, const int global_ny,
                               const int local_nx, const int local_ny,
                               const int pad, const int x_off, const int y_off,
                               const int rank, const int nranks, int* neighbours,
                               double* local_arr, const char* name, const int tt,
                               const double elapsed_sim_time) {
-  (void)global_nx; (void)global_ny; (void)local_nx; (void)local_ny; (void)pad;
-  (void)x_off; (void)y_off; (void)rank; (void)nranks; (void)neighbours;
-  (void)local_arr; (void)tt; (void)elapsed_sim_time;
-  fprintf(stderr, "arch-lite: VisIt dump of '%s' skipped (not implemented)\n", name);
+  (void)global_nx; (void)global_ny; (void)pad; (void)x_off; (void)y_off; (void)nranks;
+  (void)neighbours; (void)tt;
+  if (rank != MASTER) return;
+  const size_t n = (size_t)local_nx * (size_t)local_ny;
+  double* staged = NULL;
+  allocate_host_data(&staged, n);
+  copy_buffer(n, &local_arr, &staged, RECV);
+  char path[256];
+  snprintf(path, sizeof(path), "%s.dat", name);
+  FILE* fp = fopen(path, "wb");
+  if (!fp || fwrite(staged, sizeof(double), n, fp) != n) {
+    TERMINATE("Could not write the VisIt dump %s", path);
+  }
+  fclose(fp);
+  deallocate_host_data(staged);
+  snprintf(path, sizeof(path), "%s.bov", name);
+  fp = fopen(path, "w");
+  if (!fp) {
+    TERMINATE("Could not write the VisIt dump %s", path);
+  }
+  fprintf(fp, "TIME: %.12e\nDATA_FILE: %s.dat\nDATA_SIZE: %d %d 1\nDATA_FORMAT: DOUBLE\n"
+              "VARIABLE: %s\nDATA_ENDIAN: LITTLE\nCENTERING: zonal\n"
+              "BRICK_ORIGIN: 0. 0. 0.\nBRICK_SIZE: 1. 1. 1.\n",
+          elapsed_sim_time, name, local_nx, local_ny, name);
+  fclose(fp);
 }
 
 int within_tolerance(const double expected, const double result,

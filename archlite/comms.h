@@ -22,7 +22,7 @@ double reduce_all_sum(double local_val);
 double reduce_all_min(double local_val);
 double reduce_all_max(double local_val);
 
-/* VisIt dump of one cell-centred field: stub (all decks set visit_dump 0). */
+/* VisIt dump of one cell-centred field: <name>.bov + <name>.dat (Brick of Values). */
 void write_all_ranks_to_visit(const int global_nx, const int global_ny,
                               const int local_nx, const int local_ny,
                               const int pad, const int x_off, const int y_off,

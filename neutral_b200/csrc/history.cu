@@ -62,6 +62,21 @@ struct Parked {
 #else
 #define NB_HISTORY_BOUNDS __launch_bounds__(kHistoryThreads, NB_HISTORY_MIN_BLOCKS)
 #endif
+#ifdef NB_TRACE_WARPS
+// Measurement build (never the product): every warp records when it started and ended, on
+// which SM, and what it did (tools/warp_trace.py turns that into a timeline of the launch).
+// NB200_DEFINES=-DNB_TRACE_WARPS NB200_LIB=libneutral_b200.trace.so python -m neutral_b200.build
+__device__ unsigned long long* g_warp_trace = nullptr;  // 6 words per warp of the grid
+extern "C" int nb200_debug_set_warp_trace(void* p) {
+  return (int)cudaMemcpyToSymbol(g_warp_trace, &p, sizeof(p));
+}
+__device__ __forceinline__ unsigned long long trace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
+
 template <bool kFastDiv, bool kPreReduce>
 __global__ void NB_HISTORY_BOUNDS
 k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
@@ -77,6 +92,9 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned nf = 0, census = 0, processed = 0, died = 0;
   PARKED(nc) = 0;
+#ifdef NB_TRACE_WARPS
+  const unsigned long long trace_t0 = trace_now();
+#endif
 
   int4 m = make_int4(0, 0, 1, 0);
   if (slot < (int)*n_live) m = a.bank.meta[slot];
@@ -357,6 +375,17 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
     if (a.p_collisions) a.p_collisions[origin] += PARKED(nc);
     if (a.p_census) a.p_census[origin] += census;
   }
+#ifdef NB_TRACE_WARPS
+  if (g_warp_trace) {
+    const unsigned long long wf = warp_sum(nf), wc = warp_sum(PARKED(nc)), wp = warp_sum(processed);
+    if ((threadIdx.x & 31) == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      unsigned long long* t = g_warp_trace + 6ull * (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+      t[0] = trace_t0; t[1] = trace_now(); t[2] = smid; t[3] = wf; t[4] = wc; t[5] = wp;
+    }
+  }
+#endif
   flush_totals(a.totals, nf, PARKED(nc), processed, census, died);
 #undef PARKED
 #undef NB_CELL

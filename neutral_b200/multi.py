@@ -169,3 +169,62 @@ class GpuShardEngine:
 
     def drain(self) -> None:
         self.torch.cuda.current_stream().wait_stream(self.side)
+
+
+# ----------------------------------------------------------------------------------------
+# The owned-slice protocol of the library's own collective (csrc/nb_group.cuh), restated over
+# torch.distributed. The CUDA path does this inside libneutral_b200.so with one peer-memory
+# kernel per rank and timestep; this restatement is what the CPU tests drive over `gloo` (with
+# the oracle as the per-rank engine) to pin the slicing, the padding and the flush.
+# ----------------------------------------------------------------------------------------
+
+def owned_slice_layout(ncells: int, nranks: int):
+    """(chunk, padded): cells per owned slice - even, so that 16-byte vector accesses never
+    straddle two owners - and the padded tally length nranks * chunk (group_layout, capi.cu)."""
+    chunk = (ncells + nranks - 1) // nranks
+    chunk = (chunk + 1) & ~1
+    return chunk, chunk * nranks
+
+
+class OwnedSliceTally:
+    """Rank ``rank``'s part of a tally shared by ``world`` ranks: it owns cells
+    [rank * chunk, (rank + 1) * chunk) of the cumulative tally. ``reduce_fold`` takes every
+    rank's delta of one timestep (reduce-scatter, summed in rank order, folded into the owned
+    slice); ``flush`` adds all owned slices into a caller-visible tally (all-gather) and clears
+    them."""
+
+    def __init__(self, ncells: int, rank: int, world: int, dist=None):
+        import torch
+        self.torch = torch
+        self.ncells, self.rank, self.world, self.dist = ncells, rank, world, dist
+        self.chunk, self.padded = owned_slice_layout(ncells, world)
+        self.owned = torch.zeros(self.chunk, dtype=torch.float64)
+
+    def reduce_fold(self, delta) -> None:
+        """delta: this rank's per-timestep tally (ncells doubles, torch); cleared afterwards."""
+        torch = self.torch
+        padded = torch.zeros(self.padded, dtype=torch.float64)
+        padded[:self.ncells] = delta
+        if self.world > 1:
+            # reduce-scatter spelled with point-to-point reductions (gloo has no reduce_scatter):
+            # slice r of every rank's delta is summed on rank r
+            for r in range(self.world):
+                part = padded[r * self.chunk:(r + 1) * self.chunk].clone()
+                self.dist.reduce(part, dst=r)
+                if r == self.rank:
+                    self.owned += part
+        else:
+            self.owned += padded[:self.chunk]
+        delta.zero_()
+
+    def flush(self, tally) -> None:
+        """tally (ncells doubles, torch) += every rank's owned slice; owned slices cleared."""
+        torch = self.torch
+        if self.world > 1:
+            parts = [torch.zeros(self.chunk, dtype=torch.float64) for _ in range(self.world)]
+            self.dist.all_gather(parts, self.owned)
+            whole = torch.cat(parts)
+        else:
+            whole = self.owned
+        tally += whole[:self.ncells]
+        self.owned.zero_()

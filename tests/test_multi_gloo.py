@@ -164,3 +164,64 @@ def test_shard_ranges_tile_the_bank():
             assert first == nxt and count in (n // world, n // world + 1)
             nxt = first + count
         assert nxt == n
+
+
+# ------------------------------------------------------------------------------------------
+# The owned-slice protocol of the library's own collective (csrc/nb_group.cuh), over gloo
+# ------------------------------------------------------------------------------------------
+
+def _owned_worker(rank, world, port_no, deck, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from neutral_b200.multi import OwnedSliceTally
+        prob = build_problem(deck)
+        d = prob.deck
+        eng = OracleShardEngine(prob, rank, world)
+        group = OwnedSliceTally(d.nx * d.ny, rank, world, dist)
+        tally = torch.zeros(d.nx * d.ny, dtype=torch.float64)
+        counts = []
+        for tt in range(1, d.iterations + 1):
+            counts.append(eng.step_into_delta(tt, 0))
+            group.reduce_fold(eng.delta[0])       # every timestep: reduce-scatter + fold
+            if tt == 2:
+                group.flush(tally)                # somebody looks at the tally mid-run
+        group.flush(tally)
+        assert not bool(group.owned.any())
+        g = global_counts(counts, world, dist)
+        if rank == 0:
+            out.put(([(c.facets, c.collisions, c.processed) for c in g], tally.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,deck", [(2, "mixed_small"), (3, "csp_small")])
+def test_owned_slice_protocol_equals_single_rank(world, deck):
+    """Reduce-scatter into owned slices every timestep + all-gather when the tally is looked
+    at (the protocol of csrc/nb_group.cuh, ragged last slice included: 80 x 80 = 6400 cells
+    over 3 ranks -> chunk 2134) reproduces the single-rank run: exact counts, tally to 1e-12."""
+    from neutral_b200.multi import owned_slice_layout
+    from oracle.oracle import OraclePort
+    assert owned_slice_layout(16_000_000, 8) == (2_000_000, 16_000_000)
+    assert owned_slice_layout(6400, 3) == (2134, 6402)
+    assert owned_slice_layout(9, 2) == (6, 12)
+    prob = build_problem(deck)
+    d = prob.deck
+    port = OraclePort()
+    bank = port.inject(prob)
+    want_tally = np.zeros(d.nx * d.ny)
+    want = [port.step(prob, bank, tt, want_tally) for tt in range(1, d.iterations + 1)]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port_no = _free_port()
+    procs = [ctx.Process(target=_owned_worker, args=(r, world, port_no, deck, out))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    got_counts, got_tally = out.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got_counts == want
+    assert np.all(np.abs(got_tally - want_tally) <=
+                  1e-12 * np.maximum(np.abs(got_tally), np.abs(want_tally)))
