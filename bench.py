@@ -316,7 +316,8 @@ def golden_for(deck, nglobal):
     except (OSError, ValueError):
         return None, None
     from neutral_b200.decks import load_deck
-    key = deck.name if nglobal == load_deck(deck.name).nparticles else f"{deck.name}@{nglobal}"
+    base = deck.name[:-len("_scaled")] if deck.name.endswith("_scaled") else deck.name
+    key = base if nglobal == load_deck(base).nparticles else f"{base}@{nglobal}"
     return g.get(key), key
 
 
@@ -391,8 +392,10 @@ def time_other_decks(lib, torch, names):
             sim = Simulation(prob, per_particle_counters=False)
             sim.inject()
             snap = _soa_p()
-            st = sim.bank_to_host().as_struct()
+            injected = sim.bank_to_host()  # must outlive as_struct(): the struct aliases it
+            st = injected.as_struct()
             _check(lib.nb200_bank_create(C.byref(st), sim.count, sim.pid0, C.byref(snap)), "snap")
+            del injected
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             res = []
             for i in range(3):

@@ -381,7 +381,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
     if ((threadIdx.x & 31) == 0) {
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      unsigned long long* t = g_warp_trace + 6ull * (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+      unsigned long long* t = g_warp_trace + 6ull * (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));  // dispatch order
       t[0] = trace_t0; t[1] = trace_now(); t[2] = smid; t[3] = wf; t[4] = wc; t[5] = wp;
     }
   }

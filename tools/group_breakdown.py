@@ -39,7 +39,8 @@ ncells = d.nx * d.ny
 sim = Simulation(prob, rank=rank, nranks=world, per_particle_counters=False)
 sim.inject()
 snap = _soa_p()
-st = sim.bank_to_host().as_struct()
+injected = sim.bank_to_host()  # must outlive as_struct(): the struct aliases its arrays
+st = injected.as_struct()
 _check(lib.nb200_bank_create(C.byref(st), sim.count, sim.pid0, C.byref(snap)), "snapshot")
 rows = []
 
