@@ -455,6 +455,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
         if lib.nb200_set_option(k.encode(), int(v)) == NB200_BAD_OPTION:
             sys.exit(f"bad library option {k}={v}: {lib.nb200_last_error().decode()}")
     pipeline = int(opts.get("pipeline", 1))
+    reduce_every = lib.nb200_get_option(b"tally_reduce_every")
 
     deck = load_deck(args.deck)
     nglobal = global_particles(deck, args, world)
@@ -754,9 +755,14 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(deck, nglobal, world, args.scaling),
-        "run": {"parallelism": f"particle-sharded x{world}: {collective} per timestep beside "
-                               "the next timestep's transport, all-gather into the tally once "
-                               "per deck run" if world > 1 else "single GPU",
+        "run": {"parallelism": (f"particle-sharded x{world}: private tally buffers combined by the "
+                                f"library's {collective} "
+                                + ("once per deck run, when the tally is read"
+                                   if reduce_every == 0 else
+                                   f"every {reduce_every} timestep(s) beside the next timestep's "
+                                   "transport")
+                                + ", all-gather into the caller's tally once per deck run")
+                if world > 1 else "single GPU",
                 "options": args.opts or "defaults (pipeline=1,fast_div=1,tile_shift=8,"
                                         "length_bins=512)",
                 "timesteps_in_flight": 3,

@@ -255,6 +255,10 @@ int nb200_accumulate_clear_async(double* dst_device, double* src_device, size_t 
  * "collective" (how a sharded run combines its tally: 1, default: the library's own
  * peer-memory reduce-scatter kernel, csrc/nb_group.cuh; 0: NCCL reduce-scatter, bound at run
  * time; environment NB200_COLLECTIVE=nccl); "reduce_ctas" (grid of that kernel);
+ * "tally_reduce_every" (timesteps a sharded run deposits into its private buffers between
+ * reduce-scatters: 0, default: only when the tally is looked at - validate, downloads,
+ * nb200_tally_sync -, which is all the reference's driver needs; 1: every timestep, beside the
+ * next timestep's transport; n: every n timesteps);
  * "host_mirror" (see inject_particles); "headroom_pct" (extra bank slots in percent).
  * "tally_prereduce" = 1 implies "fast_div" = 1 (it has no separate IEEE-division build).
  * Options are process-wide defaults; nb200_bank_set_option overrides one for one bank (the
@@ -286,9 +290,10 @@ uint64_t nb200_kernel_launches(void);
  * 5. Particle-sharded runs. Histories are independent and keyed by the GLOBAL
  *    particle index (omp3/neutral.c:632-641), so GPU g of G transports the contiguous range of
  *    omp3's thread split (omp3/neutral.c:64-74) and only the additive tally is combined: each
- *    GPU deposits a timestep into a private delta, and one library kernel per GPU reads its
- *    slice of every peer's delta over NVLink and folds the sum into the slice of the
- *    cumulative tally it owns (csrc/nb_group.cuh), beside the next timestep's transport.
+ *    GPU deposits into a private buffer, and one library kernel per GPU reads its slice of
+ *    every peer's buffer over NVLink and folds the sum into the slice of the cumulative tally
+ *    it owns (csrc/nb_group.cuh) - when the tally is looked at, or every
+ *    "tally_reduce_every" timesteps beside the next timestep's transport.
  *    Two ways to get there:
  *      - one process, several GPUs: option "ngpus" / NB200_NGPUS before inject_particles.
  *        Nothing else changes for the caller (this is how `NB200_NGPUS=8 ./neutral.b200 ...`

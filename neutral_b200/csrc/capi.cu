@@ -42,6 +42,7 @@ const OptionSpec kOptionSpecs[] = {
     {"ngpus", &Options::ngpus, 0, kMaxRanks},
     {"collective", &Options::collective, 0, 1},
     {"reduce_ctas", &Options::reduce_ctas, 1, 8192},
+    {"tally_reduce_every", &Options::tally_reduce_every, 0, 1000000},
     {"host_mirror", &Options::host_mirror, 0, 1},
     {"headroom_pct", &Options::headroom_pct, 0, 1000},
 };
@@ -772,7 +773,9 @@ void group_alloc_member(TallyGroup& g, int rank, int dev) {
   CU_FATAL(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   // the collective of timestep t runs beside the transport of timestep t+1: let its (few,
   // small) CTAs in whenever an SM has room
-  CU_FATAL(cudaStreamCreateWithPriority(&m.side, cudaStreamNonBlocking, hi));
+  const char* prio = getenv("NB200_SIDE_PRIORITY");  // measurement knob: 0 = default priority
+  CU_FATAL(cudaStreamCreateWithPriority(&m.side, cudaStreamNonBlocking,
+                                        prio && atoi(prio) == 0 ? lo : hi));
   for (int k = 0; k < kDeltaBuffers; ++k) {
     CU_FATAL(cudaEventCreateWithFlags(&m.ev_hist[k], cudaEventDisableTiming));
     CU_FATAL(cudaEventCreateWithFlags(&m.ev_zeroed[k], cudaEventDisableTiming));
@@ -811,6 +814,7 @@ TallyGroup* group_create_local(const Bank* bank, size_t ncells) {
   g->ncells = ncells;
   g->collective = opt_of(bank, &Options::collective);
   g->reduce_ctas = opt_of(bank, &Options::reduce_ctas);
+  g->reduce_every = opt_of(bank, &Options::tally_reduce_every);
   if (g->collective) {  // the peer-memory kernel needs every pair of GPUs peer-mapped
     for (const Shard& a : bank->shards)
       for (const Shard& b : bank->shards) {
@@ -855,6 +859,20 @@ TallyGroup* group_create_local(const Bank* bank, size_t ncells) {
   return g;
 }
 
+// What rank `rank` waits for: 0 = every rank's `ready`, 1 = the `consumed` flags in its own
+// block, 2 = every rank's `flush_ready`, 3 = the `flush_consumed` flags in its own block.
+WaitList wait_list(const TallyGroup& g, int rank, int what) {
+  WaitList w{};
+  w.n = g.nranks;
+  w.fault = &g.m[rank].sync->fault;
+  for (int d = 0; d < g.nranks; ++d)
+    w.flag[d] = what == 0   ? &g.m[d].sync->ready
+                : what == 1 ? &g.m[rank].sync->consumed[d]
+                : what == 2 ? &g.m[d].sync->flush_ready
+                            : &g.m[rank].sync->flush_consumed[d];
+  return w;
+}
+
 GroupView group_view(const TallyGroup& g, int rank, int k, bool owned_slices) {
   GroupView v{};
   v.nranks = g.nranks;
@@ -868,16 +886,26 @@ GroupView group_view(const TallyGroup& g, int rank, int k, bool owned_slices) {
   return v;
 }
 
-// The collective half of epoch `epoch` for every LOCAL member, queued on the members' side
-// streams behind their history kernels (ev_hist): reduce-scatter of the delta fused with the
-// fold into the owned slice, then the delta buffer is cleared for its reuse in three epochs.
-void group_enqueue_collective(TallyGroup& g, unsigned long long epoch) {
-  const int k = (int)(epoch % kDeltaBuffers);
+// Reduction number `g.epoch + 1` of the deposit buffer in use, for every LOCAL member, queued
+// on the members' side streams behind the last history kernel that deposited into it (ev_hist):
+// reduce-scatter of the buffer fused with the fold into the owned slice, then the buffer is
+// cleared for its next turn and the ranks move on to the next of the three buffers.
+// `signalled`: the last timestep's publish kernel already raised `ready` to this epoch (a
+// reduction that was known when the timestep was enqueued); otherwise it is raised here.
+void group_reduce(TallyGroup& g, bool signalled) {
+  if (g.steps_deposited == 0) return;
+  const unsigned long long epoch = ++g.epoch;
+  const int k = g.cur_k;
   const NcclApi* api = g.collective ? nullptr : nccl_api(nullptr);
   for (int r = 0; r < g.nranks; ++r) {
     GroupMember& m = g.m[r];
     if (m.dev < 0) continue;
     DeviceGuard guard(m.dev);
+    if (!signalled && g.collective) {
+      DeviceCtx& c = ctx_on(m.dev);
+      c.launches += launch_signal(m.sync, 0, epoch, c.stream);
+      CU_FATAL(cudaEventRecord(m.ev_hist[k], c.stream));
+    }
     CU_FATAL(cudaStreamWaitEvent(m.side, m.ev_hist[k], 0));
   }
   if (g.collective) {
@@ -886,9 +914,12 @@ void group_enqueue_collective(TallyGroup& g, unsigned long long epoch) {
       if (m.dev < 0) continue;
       DeviceGuard guard(m.dev);
       DeviceCtx& c = ctx_on(m.dev);
+      c.launches += launch_wait_flags(wait_list(g, r, 0), epoch, m.side);
       c.launches += launch_reduce_fold(group_view(g, r, k, false), m.owned, epoch, g.reduce_ctas,
                                        m.side);
-      c.launches += launch_wait_zero(m.sync, g.nranks, 0, m.delta[k], g.padded, epoch, m.side);
+      // every rank has read its slice of this delta: clear it for its reuse in three epochs
+      c.launches += launch_wait_flags(wait_list(g, r, 1), epoch, m.side);
+      CU_FATAL(cudaMemsetAsync(m.delta[k], 0, g.padded * 8, m.side));
       CU_FATAL(cudaGetLastError());
     }
   } else {
@@ -918,6 +949,8 @@ void group_enqueue_collective(TallyGroup& g, unsigned long long epoch) {
     CU_FATAL(cudaEventRecord(m.ev_zeroed[k], m.side));
     m.zeroed_recorded[k] = true;
   }
+  g.cur_k = (k + 1) % kDeltaBuffers;
+  g.steps_deposited = 0;
   g.dirty = true;
 }
 
@@ -939,6 +972,7 @@ void group_check_fault(TallyGroup& g) {
 // collective: every rank must call it the same number of times.
 void group_flush(TallyGroup& g) {
   if (!g.dirty || !g.target) return;
+  group_reduce(g, false);  // whatever has been deposited since the last reduction
   const NcclApi* api = g.collective ? nullptr : nccl_api(nullptr);
   const unsigned long long fe = ++g.flush_epoch;
   const int primary = g.mp ? g.mp_rank : 0;
@@ -954,10 +988,12 @@ void group_flush(TallyGroup& g) {
     GroupMember& m = g.m[primary];
     DeviceGuard guard(m.dev);
     DeviceCtx& c = ctx_on(m.dev);
+    if (g.mp) c.launches += launch_wait_flags(wait_list(g, primary, 2), fe, m.side);
     c.launches += launch_gather_owned(group_view(g, primary, 0, true), g.target, g.mp ? fe : 0,
                                       m.side);
     if (g.mp) {
-      c.launches += launch_wait_zero(m.sync, g.nranks, 1, m.owned, g.chunk, fe, m.side);
+      c.launches += launch_wait_flags(wait_list(g, primary, 3), fe, m.side);
+      CU_FATAL(cudaMemsetAsync(m.owned, 0, g.chunk * 8, m.side));
       CU_FATAL(cudaStreamSynchronize(m.side));
     } else {
       CU_FATAL(cudaStreamSynchronize(m.side));
@@ -1049,16 +1085,22 @@ void enqueue_step(Bank* bank, const StepRequest& rq) {
       terminate("solve_transport_2d: the multi-process group was created for %zu cells, the "
                 "mesh has %zu", group->ncells, ncells);
   }
+  // In a group every rank deposits into a private buffer; the buffers are reduce-scattered into
+  // the owned slices every `reduce_every` timesteps, or - the default - only when somebody looks
+  // at the tally: nothing on this path reads the tally between timesteps (main.c touches it in
+  // validate and in VisIt dumps only), and a collective that is not run costs nothing.
   unsigned long long epoch = 0;
   int k = 0;
+  bool closes = false;
   if (group) {
     if (group->target != rq.tally) {  // a different caller tally: settle the old one first
       group_flush(*group);
       group->target = rq.tally;
       group->target_dev = bank->primary_dev;
     }
-    epoch = ++group->epoch;
-    k = (int)(epoch % kDeltaBuffers);
+    k = group->cur_k;
+    closes = group->reduce_every > 0 && group->steps_deposited + 1 >= group->reduce_every;
+    epoch = group->epoch + 1;
   }
   PendingStep ps;
   ps.pipeline = opt_of(bank, &Options::pipeline) != 0;
@@ -1094,8 +1136,8 @@ void enqueue_step(Bank* bank, const StepRequest& rq) {
       const int rank = group->mp ? group->mp_rank : (int)si;
       GroupMember& m = group->m[rank];
       io.tally = m.delta[k];
-      if (group->collective) sync = m.sync;
-      // the buffer was cleared behind its last collective, on the side stream
+      if (group->collective && closes) sync = m.sync;  // this timestep's publish raises `ready`
+      // the buffer was cleared behind its last reduction, on the side stream
       if (m.zeroed_recorded[k]) CU_FATAL(cudaStreamWaitEvent(c.stream, m.ev_zeroed[k], 0));
       enqueue_shard_step(c, bank, sh, rq, io, slot, sync, epoch);
       CU_FATAL(cudaEventRecord(m.ev_hist[k], c.stream));
@@ -1103,7 +1145,11 @@ void enqueue_step(Bank* bank, const StepRequest& rq) {
       enqueue_shard_step(c, bank, sh, rq, io, slot, nullptr, 0);
     }
   }
-  if (group) group_enqueue_collective(*group, epoch);
+  if (group) {
+    group->steps_deposited++;
+    group->dirty = true;
+    if (closes) group_reduce(*group, true);
+  }
   bank->pending.push_back(ps);
   g_last_deferred = bank;
 }
@@ -2072,6 +2118,7 @@ extern "C" int nb200_mp_init(int nranks, int rank, size_t ncells, void* blob_out
   g->ncells = ncells;
   g->collective = g_opt.collective;
   g->reduce_ctas = g_opt.reduce_ctas;
+  g->reduce_every = g_opt.tally_reduce_every;
   g->mp = true;
   g->mp_rank = rank;
   group_layout(*g);

@@ -46,7 +46,8 @@ struct Options {
   int history_smem_pad = 0;
   int ngpus = 0;         // GPUs the next inject_particles / nb200_bank_create shards over (0/1: one)
   int collective = 1;    // 1: the library's peer-memory reduce-scatter kernel; 0: NCCL
-  int reduce_ctas = 296; // grid of the peer-memory reduce kernel
+  int reduce_ctas = 592; // grid of the peer-memory reduce kernel
+  int tally_reduce_every = 0;  // timesteps between reduce-scatters of a sharded tally; 0: on demand
   int host_mirror = 0;   // keep a host copy of the bank behind the handle's 11 pointers
   int headroom_pct = 0;  // extra bank capacity for produced particles (omp3/neutral.c:570: 100)
 };
@@ -171,9 +172,12 @@ struct TallyGroup {
   int collective = 1;
   bool mp = false;
   int mp_rank = -1;
-  int reduce_ctas = 296;
+  int reduce_ctas = 592;
+  int reduce_every = 0;      // timesteps deposited into one buffer before it is reduced (0: on demand)
+  int steps_deposited = 0;   // timesteps in the current deposit buffer, not reduced yet
+  int cur_k = 0;             // the deposit buffer in use
   GroupMember m[kMaxRanks];
-  unsigned long long epoch = 0, flush_epoch = 0;
+  unsigned long long epoch = 0, flush_epoch = 0;  // reductions / flushes so far
   double* target = nullptr;  // the caller-visible tally the owned slices belong to
   int target_dev = -1;
   bool dirty = false;        // owned slices hold contributions the target has not received

@@ -21,20 +21,30 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // Spins until *flag >= want. Bounded: after kWaitTimeoutNs the wait gives up and raises
-// *fault (the results of this timestep are then wrong and the host says so).
+// *fault (the results of this timestep are then wrong and the host says so). The loop polls
+// with RELAXED loads and acquires once at the end: an acquire per poll invalidates the SM's L1
+// every few hundred nanoseconds, under the history kernel that shares the SM.
 __device__ __forceinline__ void wait_at_least(const unsigned long long* flag,
                                               unsigned long long want,
                                               unsigned long long* fault) {
-  if (ld_acquire_sys(flag) >= want) return;
-  const unsigned long long t0 = global_timer_ns();
-  while (ld_acquire_sys(flag) < want) {
-    __nanosleep(256);
-    if (global_timer_ns() - t0 > kWaitTimeoutNs) {
-      atomicExch(fault, 1ull);
-      return;
+  if (ld_relaxed_sys(flag) < want) {
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_relaxed_sys(flag) < want) {
+      __nanosleep(512);
+      if (global_timer_ns() - t0 > kWaitTimeoutNs) {
+        atomicExch(fault, 1ull);
+        return;
+      }
     }
   }
+  (void)ld_acquire_sys(flag);
 }
 
 // The CTA that finishes last runs `then` (one election counter per kernel kind).
@@ -57,14 +67,16 @@ __device__ __forceinline__ bool last_cta(unsigned int* counter) {
 // an SM whose register file holds six CTAs of the history kernel, so the collective of
 // timestep t runs on the SMs while the transport of timestep t+1 owns them.
 // ------------------------------------------------------------------------------------
+// One warp waits for the flags; the kernels behind it in stream order then find their inputs
+// ready without hundreds of CTAs polling (and without any of them sitting on an SM, spinning,
+// beside the transport).
+__global__ void k_wait_flags(const WaitList w, unsigned long long want) {
+  if ((int)threadIdx.x < w.n) wait_at_least(w.flag[threadIdx.x], want, w.fault);
+}
+
 __global__ void __launch_bounds__(128, 16)
 k_reduce_fold(const GroupView g, double* __restrict__ owned, unsigned long long epoch) {
   SyncBlock* mine = g.sync[g.rank];
-  if (epoch) {
-    if ((int)threadIdx.x < g.nranks)
-      wait_at_least(&g.sync[threadIdx.x]->ready, epoch, &mine->fault);
-    __syncthreads();
-  }
   const size_t begin = (size_t)g.rank * g.chunk;
   const size_t end = begin + g.chunk < g.ncells ? begin + g.chunk : g.ncells;
   const size_t count = end > begin ? end - begin : 0;
@@ -96,33 +108,12 @@ k_reduce_fold(const GroupView g, double* __restrict__ owned, unsigned long long 
   }
 }
 
-__global__ void __launch_bounds__(256)
-k_wait_zero(SyncBlock* mine, int nranks, int flush, double* __restrict__ buf, size_t n,
-            unsigned long long epoch) {
-  if (epoch) {
-    if ((int)threadIdx.x < nranks)
-      wait_at_least(flush ? &mine->flush_consumed[threadIdx.x] : &mine->consumed[threadIdx.x],
-                    epoch, &mine->fault);
-    __syncthreads();
-  }
-  const size_t pairs = n >> 1;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  double2* b2 = reinterpret_cast<double2*>(buf);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride)
-    b2[i] = make_double2(0.0, 0.0);
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) buf[n - 1] = 0.0;
-}
 
 // All-gather fused with the accumulation into the caller-visible tally: slice by slice,
 // straight out of the owners' memory.
 __global__ void __launch_bounds__(256)
 k_gather_owned(const GroupView g, double* __restrict__ tally, unsigned long long epoch) {
   SyncBlock* mine = g.sync[g.rank];
-  if (epoch) {
-    if ((int)threadIdx.x < g.nranks)
-      wait_at_least(&g.sync[threadIdx.x]->flush_ready, epoch, &mine->fault);
-    __syncthreads();
-  }
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (int d = 0; d < g.nranks; ++d) {
     const size_t begin = (size_t)d * g.chunk;
@@ -163,13 +154,12 @@ k_fold_plain(double* __restrict__ dst, const double* __restrict__ src, size_t n)
 
 int launch_reduce_fold(const GroupView& g, double* owned, unsigned long long epoch, int ctas,
                        cudaStream_t st) {
-  k_reduce_fold<<<ctas > 0 ? ctas : 296, 128, 0, st>>>(g, owned, epoch);
+  k_reduce_fold<<<ctas > 0 ? ctas : 592, 128, 0, st>>>(g, owned, epoch);
   return 1;
 }
 
-int launch_wait_zero(SyncBlock* mine, int nranks, int flush, double* buf, size_t n,
-                     unsigned long long epoch, cudaStream_t st) {
-  k_wait_zero<<<148, 256, 0, st>>>(mine, nranks, flush, buf, n, epoch);
+int launch_wait_flags(const WaitList& w, unsigned long long want, cudaStream_t st) {
+  k_wait_flags<<<1, 32, 0, st>>>(w, want);
   return 1;
 }
 

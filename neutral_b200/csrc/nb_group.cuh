@@ -54,14 +54,20 @@ struct GroupView {
   SyncBlock* sync[kMaxRanks];
 };
 
-// rank's slice: owned[i] += sum_d delta_d[rank * chunk + i]; epoch 0 = no flag traffic (the
-// host already ordered everything: single-process flushes).
+// Flags one warp waits for (k_wait_flags) before the kernels behind it on the stream run.
+struct WaitList {
+  int n;
+  const unsigned long long* flag[kMaxRanks];
+  unsigned long long* fault;
+};
+int launch_wait_flags(const WaitList& w, unsigned long long want, cudaStream_t st);
+// rank's slice: owned[i] += sum_d delta_d[rank * chunk + i], behind a wait for every rank's
+// `ready`; at the end the rank reports `consumed[rank] = epoch` into every rank's block.
+// epoch 0 = no flag traffic (the host already ordered everything: single-process flushes).
 int launch_reduce_fold(const GroupView& g, double* owned, unsigned long long epoch, int ctas,
                        cudaStream_t st);
-// Waits until every rank has consumed `epoch` of this rank's delta, then clears it.
-int launch_wait_zero(SyncBlock* mine, int nranks, int flush, double* buf, size_t n,
-                     unsigned long long epoch, cudaStream_t st);
-// tally[i] += owned_{i / chunk}[i % chunk] for every cell (g.src = owned slices).
+// tally[i] += owned_{i / chunk}[i % chunk] for every cell (g.src = owned slices), behind a wait
+// for every rank's `flush_ready`; reports `flush_consumed[rank] = epoch` at the end.
 int launch_gather_owned(const GroupView& g, double* tally, unsigned long long epoch,
                         cudaStream_t st);
 // Raises sync->ready (flush = 0) or sync->flush_ready (flush = 1) to `epoch`, release-ordered

@@ -241,9 +241,10 @@ def _need_gpus(lib, n):
         pytest.skip(f"needs {n} GPUs, {lib.nb200_device_count()} visible")
 
 
+@pytest.mark.parametrize("reduce_every", [0, 1, 2])
 @pytest.mark.parametrize("collective", [1, 0])
 @pytest.mark.parametrize("deck", ["mixed_small", "csp_small"])
-def test_bank_sharded_over_gpus_inside_the_library(gpu_lib, port, deck, collective):
+def test_bank_sharded_over_gpus_inside_the_library(gpu_lib, port, deck, collective, reduce_every):
     """One process, several GPUs (option ngpus): same calls as a single-GPU run; the shards
     replay their particles bit for bit, the counts are the sums, the per-particle counters land
     in the caller's arrays, and the tally (reduce-scattered into owned slices every timestep,
@@ -253,6 +254,7 @@ def test_bank_sharded_over_gpus_inside_the_library(gpu_lib, port, deck, collecti
     prob = build_problem(deck)
     d = prob.deck
     prev = gpu_lib.nb200_set_option(b"collective", collective)
+    prev_every = gpu_lib.nb200_set_option(b"tally_reduce_every", reduce_every)
     try:
         sim = Simulation(prob, ngpus=ngpus, per_particle_counters=bool(collective))
         sim.inject()
@@ -274,6 +276,7 @@ def test_bank_sharded_over_gpus_inside_the_library(gpu_lib, port, deck, collecti
         sim.free()
     finally:
         gpu_lib.nb200_set_option(b"collective", prev)
+        gpu_lib.nb200_set_option(b"tally_reduce_every", prev_every)
 
 
 def test_sharded_full_deck_matches_the_reference(gpu_lib):

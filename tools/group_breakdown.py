@@ -6,9 +6,11 @@
 
 One deck run per mode, device time (max over ranks), best of 3, next to rank 0's own history-
 and sort-kernel time: (a) transport only - no collective at all, every rank into its own tally;
-(b) the library's peer-memory reduce-scatter kernel every timestep + the all-gather at the end
-(the default); (c) the same with NCCL's reduce-scatter inside the library; (d) round 1's host
-loop: torch all-reduce of the whole delta + fold on a side stream (neutral_b200/multi.py).
+(b) the library group with its peer-memory reduce-scatter kernel, reduced on demand (the default:
+once per deck run, when the tally is read) and every timestep (beside the next timestep's
+transport), each followed by the all-gather into the caller's tally; (c) the same with NCCL's
+reduce-scatter inside the library; (d) round 1's host loop: torch all-reduce of the whole delta
++ fold on a side stream (neutral_b200/multi.py).
 """
 import ctypes as C
 import os
@@ -84,15 +86,17 @@ def pipelined_and_sync():
 
 
 report("transport only (no collective)", timed(pipelined))
-for flavour, name in ((1, "library group: peer-memory reduce-scatter kernel"),
-                      (0, "library group: NCCL reduce-scatter")):
+for flavour, every, name in ((1, 0, "library group: peer-memory kernel, reduce on demand"),
+                             (1, 1, "library group: peer-memory kernel, every timestep"),
+                             (0, 0, "library group: NCCL, reduce on demand"),
+                             (0, 1, "library group: NCCL, every timestep")):
     lib.nb200_set_option(b"collective", flavour)
+    lib.nb200_set_option(b"tally_reduce_every", every)
     what = connect_group(lib, dist, torch, world, rank, ncells)
     report(f"{name}", timed(pipelined_and_sync))
-    if rank == 0:
-        print(f"    ({what})", flush=True)
     lib.nb200_mp_finalize()
 lib.nb200_set_option(b"collective", 1)
+lib.nb200_set_option(b"tally_reduce_every", 0)
 engine = GpuShardEngine(sim, ncells)
 report("round-1 host loop: torch all-reduce + fold",
        timed(lambda: rows.extend(run_timesteps(engine, d.iterations, world, dist, overlap=True))))
