@@ -141,6 +141,11 @@ struct DeviceGuard {
   }
 };
 
+// Kernels are loaded when the CUDA context is created, not at their first launch: the first
+// timestep is timed by the reference's driver like any other (main.c:99-116). Has to be in the
+// environment before the process initialises CUDA; a host that already did keeps its own mode.
+__attribute__((constructor)) void load_kernels_eagerly() { setenv("CUDA_MODULE_LOADING", "EAGER", 0); }
+
 void read_environment() {
   if (g_env_read) return;
   g_env_read = true;
@@ -365,7 +370,13 @@ Bank* new_bank(int n, uint64_t pid0, int ngpus, int headroom_pct, bool mirror, s
     sh.n_upper = sh.n;
     sh.capacity = sh.n + (int)(((long long)sh.n * headroom_pct + 99) / 100);
     DeviceGuard guard(sh.dev);
-    total += bank_alloc(ctx_on(sh.dev), sh.cur, sh.capacity);
+    DeviceCtx& c = ctx_on(sh.dev);
+    total += bank_alloc(c, sh.cur, sh.capacity);
+    // the double buffer of the per-step sort and its keys: allocated with the bank, so that the
+    // first timestep (which main.c times like any other) does not pay for them
+    total += bank_alloc(c, sh.alt, sh.capacity);
+    total += device_zalloc(c, &sh.keys, (size_t)sh.capacity);
+    sh.has_alt = true;
     bank->shards.push_back(sh);
   }
   const uint64_t nviews = mirror ? (uint64_t)std::max(n, 1) : 1;
@@ -570,23 +581,63 @@ void stage_tables(DeviceCtx& c, StepArgs& a) {
   a.cs_a = CsStage{d_kv_a, d_bk_a, pa.bits0, pa.shift, pa.nb, a.a_n};
 }
 
-void stage_tiles(DeviceCtx& c, StepArgs& a, cudaStream_t st) {
-  const int nfine = (((a.nx - 1) >> kTileShift) + 1) * (((a.ny - 1) >> kTileShift) + 1);
-  const int ncoarse = (((a.nx - 1) >> kCoarseShift) + 1) * (((a.ny - 1) >> kCoarseShift) + 1);
+// Per-mesh staging blocks of a device (tile maps, target-edge rows) and the sort's histogram
+// for the default key space. Sized when a bank is created for a mesh (inject_particles knows
+// nx and ny), so that the first timestep - which the driver times like any other - finds them.
+void reserve_mesh_scratch(DeviceCtx& c, int nx, int ny, long long nbins) {
+  const int nfine = (((nx - 1) >> kTileShift) + 1) * (((ny - 1) >> kTileShift) + 1);
+  const int ncoarse = (((nx - 1) >> kCoarseShift) + 1) * (((ny - 1) >> kCoarseShift) + 1);
   if (c.tile_capacity < nfine + ncoarse) {
     cudaFree(c.d_tile_rho);
     CU_FATAL(cudaMalloc(&c.d_tile_rho, sizeof(double) * (nfine + ncoarse)));
     c.tile_capacity = nfine + ncoarse;
   }
-  c.launches += launch_stage_tiles(a.density, a.nx, a.ny, c.d_tile_rho, c.d_tile_rho + nfine,
-                                   &a.tiles, st);
-  // ... and the target-edge rows (same consumer: the event loop only)
-  const int stride = ((std::max(a.nx, a.ny) + 1 + 31) / 32) * 32;
+  const int stride = ((std::max(nx, ny) + 1 + 31) / 32) * 32;
   if (c.edges_capacity < 4 * stride) {
     cudaFree(c.d_edges4);
     CU_FATAL(cudaMalloc(&c.d_edges4, sizeof(double) * 4 * (size_t)stride));
     c.edges_capacity = 4 * stride;
   }
+  if (c.bins_capacity < nbins) {
+    cudaFree(c.d_bins);
+    // histogram, cursors, and one scan partial per 2048 bins
+    CU_FATAL(cudaMalloc(&c.d_bins, sizeof(unsigned) * (2 * (size_t)nbins + nbins / 2048 + 1)));
+    c.bins_capacity = nbins;
+  }
+  // the staged cross-section block for two tables of the reference's size (grown on demand)
+  const size_t cs_guess = 2 * (((sizeof(double2) * 32768) + 255) & ~(size_t)255) +
+                          2 * (((sizeof(int) * (kCsBuckets + 1)) + 255) & ~(size_t)255);
+  if (c.cs_stage_bytes < cs_guess) {
+    cudaFree(c.d_cs_stage);
+    CU_FATAL(cudaMalloc(&c.d_cs_stage, cs_guess));
+    c.cs_stage_bytes = cs_guess;
+  }
+}
+
+// The sort's key space for a mesh under the given options: 3 classes x length bins x tiles + the
+// dead bin, in 64 bits; a combination that asks for more bins than the scratch is worth gets
+// coarser tiles (a scheduling key, nothing else).
+long long sort_key_space(int nx, int ny, int length_bins, int* tile_shift, int* tiles_x,
+                         int* ntiles) {
+  const long long nq = std::max(length_bins, 1);
+  long long nt = 1, tx = 1;
+  for (;; ++*tile_shift) {
+    tx = *tile_shift >= 0 ? ((nx - 1) >> *tile_shift) + 1 : 1;
+    nt = *tile_shift >= 0 ? tx * (((ny - 1) >> *tile_shift) + 1) : 1;
+    if (*tile_shift < 0 || 3ll * nq * nt + 1 <= (1ll << 24)) break;
+  }
+  *tiles_x = (int)tx;
+  *ntiles = (int)nt;
+  return 3ll * nq * nt + 1;
+}
+
+void stage_tiles(DeviceCtx& c, StepArgs& a, cudaStream_t st) {
+  const int nfine = (((a.nx - 1) >> kTileShift) + 1) * (((a.ny - 1) >> kTileShift) + 1);
+  reserve_mesh_scratch(c, a.nx, a.ny, 0);
+  c.launches += launch_stage_tiles(a.density, a.nx, a.ny, c.d_tile_rho, c.d_tile_rho + nfine,
+                                   &a.tiles, st);
+  // ... and the target-edge rows (same consumer: the event loop only)
+  const int stride = ((std::max(a.nx, a.ny) + 1 + 31) / 32) * 32;
   c.launches += launch_stage_edges(a.edgex, a.nx, a.edgey, a.ny, stride, c.d_edges4, st);
   a.edges4 = c.d_edges4;
   a.edge_stride = stride;
@@ -672,20 +723,10 @@ void enqueue_shard_step(DeviceCtx& c, const Bank* bank, Shard& sh, const StepReq
     SortArgs s{};
     s.nq = std::max(opt_of(bank, &Options::length_bins), 1);
     s.tile_shift = opt_of(bank, &Options::tile_shift);
-    // 3 classes x length bins x tiles + the dead bin, in 64 bits; a combination that asks for
-    // more bins than the scratch is worth gets coarser tiles (a scheduling key, nothing else)
-    long long ntiles = 1, tiles_x = 1;
-    for (;; ++s.tile_shift) {
-      tiles_x = s.tile_shift >= 0 ? ((rq.nx - 1) >> s.tile_shift) + 1 : 1;
-      ntiles = s.tile_shift >= 0 ? tiles_x * (((rq.ny - 1) >> s.tile_shift) + 1) : 1;
-      if (s.tile_shift < 0 || 3ll * s.nq * ntiles + 1 <= (1ll << 24)) break;
-    }
-    s.tiles_x = (int)tiles_x;
-    s.ntiles = (int)ntiles;
+    s.nbins = (int)sort_key_space(rq.nx, rq.ny, s.nq, &s.tile_shift, &s.tiles_x, &s.ntiles);
     s.q_scale = 24.0f;  // 12 bins across the sqrt(2) spread of facet counts with direction
     s.inv_dx = (float)((double)rq.nx / mesh_w);
     s.inv_dy = (float)((double)rq.ny / mesh_h);
-    s.nbins = 3 * s.nq * s.ntiles + 1;
     s.n_upper = sh.n_upper;
     s.n = sh.n;
     if (!sh.has_alt) {
@@ -693,12 +734,7 @@ void enqueue_shard_step(DeviceCtx& c, const Bank* bank, Shard& sh, const StepReq
       device_zalloc(c, &sh.keys, (size_t)sh.capacity);
       sh.has_alt = true;
     }
-    if (c.bins_capacity < s.nbins) {
-      cudaFree(c.d_bins);
-      // histogram, cursors, and one scan partial per 2048 bins
-      CU_FATAL(cudaMalloc(&c.d_bins, sizeof(unsigned) * (2 * (size_t)s.nbins + s.nbins / 2048 + 1)));
-      c.bins_capacity = s.nbins;
-    }
+    reserve_mesh_scratch(c, rq.nx, rq.ny, s.nbins);
     s.keys = sh.keys;
     s.bin_count = c.d_bins;
     s.bin_cursor = c.d_bins + s.nbins;
@@ -1037,11 +1073,12 @@ void flush_groups_touching(const void* ptr, size_t bytes) {
   }
 }
 
-// Replica of a read-only input that lives on `primary_dev`, for device c (current).
-const double* replica_of(DeviceCtx& c, int primary_dev, const double* src, size_t count) {
+// Replica of a read-only input that lives on `primary_dev`, for shard sh on device c (current).
+const double* replica_of(DeviceCtx& c, Shard& sh, int primary_dev, const double* src,
+                         size_t count) {
   if (c.device == primary_dev || !src) return src;
   const size_t bytes = count * sizeof(double);
-  for (auto& r : c.replicas)
+  for (auto& r : sh.replicas)
     if (r.src == src && r.bytes == bytes) {
       if (r.generation != g_replica_generation) {
         CU_FATAL(cudaMemcpyPeerAsync(r.copy, c.device, src, primary_dev, bytes, c.stream));
@@ -1057,7 +1094,7 @@ const double* replica_of(DeviceCtx& c, int primary_dev, const double* src, size_
     CU_FATAL(cudaStreamSynchronize(ctx_on(primary_dev).stream));
   }
   CU_FATAL(cudaMemcpyPeerAsync(copy, c.device, src, primary_dev, bytes, c.stream));
-  c.replicas.push_back({src, bytes, copy, g_replica_generation});
+  sh.replicas.push_back({src, bytes, copy, g_replica_generation});
   return (const double*)copy;
 }
 
@@ -1117,13 +1154,13 @@ void enqueue_step(Bank* bank, const StepRequest& rq) {
     ps.slot[si] = slot;
     ShardIO io;
     const int pd = bank->primary_dev;
-    io.density = replica_of(c, pd, rq.density, ncells);
-    io.edgex = replica_of(c, pd, rq.edgex, (size_t)rq.nx + 1);
-    io.edgey = replica_of(c, pd, rq.edgey, (size_t)rq.ny + 1);
-    io.s_keys = replica_of(c, pd, rq.s_keys, (size_t)rq.s_n);
-    io.s_vals = replica_of(c, pd, rq.s_vals, (size_t)rq.s_n);
-    io.a_keys = replica_of(c, pd, rq.a_keys, (size_t)rq.a_n);
-    io.a_vals = replica_of(c, pd, rq.a_vals, (size_t)rq.a_n);
+    io.density = replica_of(c, sh, pd, rq.density, ncells);
+    io.edgex = replica_of(c, sh, pd, rq.edgex, (size_t)rq.nx + 1);
+    io.edgey = replica_of(c, sh, pd, rq.edgey, (size_t)rq.ny + 1);
+    io.s_keys = replica_of(c, sh, pd, rq.s_keys, (size_t)rq.s_n);
+    io.s_vals = replica_of(c, sh, pd, rq.s_vals, (size_t)rq.s_n);
+    io.a_keys = replica_of(c, sh, pd, rq.a_keys, (size_t)rq.a_n);
+    io.a_vals = replica_of(c, sh, pd, rq.a_vals, (size_t)rq.a_n);
     io.tally = rq.tally;
     // per-particle counters live on the primary GPU, indexed in injection order: a secondary
     // shard reaches its part of them through peer access (one 8-byte update per particle-step)
@@ -1380,13 +1417,19 @@ extern "C" size_t inject_particles(
   size_t bytes = 0;
   Bank* bank = new_bank(count, (uint64_t)first, g_opt.ngpus, g_opt.headroom_pct,
                         g_opt.host_mirror != 0, &bytes);
+  for (Shard& sh : bank->shards) {  // per-mesh scratch of every GPU involved, ahead of timestep 1
+    DeviceGuard guard(sh.dev);
+    int shift = g_opt.tile_shift, tx = 1, nt = 1;
+    const long long nbins = sort_key_space(local_nx, local_ny, g_opt.length_bins, &shift, &tx, &nt);
+    reserve_mesh_scratch(ctx_on(sh.dev), local_nx, local_ny, nbins);
+  }
   if (g_opt.device_inject) {
     // The bank is generated where it lives: no host loop, no 80-byte-per-particle upload.
     for (Shard& sh : bank->shards) {
       DeviceGuard guard(sh.dev);
       DeviceCtx& c = ctx_on(sh.dev);
-      InjectArgs ia{replica_of(c, primary.device, edgex, (size_t)local_nx + 1),
-                    replica_of(c, primary.device, edgey, (size_t)local_ny + 1), local_nx,
+      InjectArgs ia{replica_of(c, sh, primary.device, edgex, (size_t)local_nx + 1),
+                    replica_of(c, sh, primary.device, edgey, (size_t)local_ny + 1), local_nx,
                     local_ny, local_particle_left_off, local_particle_bottom_off,
                     local_particle_width, local_particle_height, dt, initial_energy};
       c.launches += launch_inject(sh.cur, sh.n, sh.pid0, ia, c.d_sct, c.stream);
@@ -1396,6 +1439,9 @@ extern "C" size_t inject_particles(
       DeviceGuard guard(sh.dev);
       CU_FATAL(cudaStreamSynchronize(ctx_on(sh.dev).stream));
     }
+    // the tally group of a sharded bank (slabs, peer mappings): built here, outside the timesteps
+    if (!single_shard(bank))
+      bank->group = group_create_local(bank, (size_t)local_nx * (size_t)local_ny);
     refresh_mirror(bank);
     *particles = handle_of(bank);
     return bytes;
@@ -1938,6 +1984,7 @@ extern "C" int nb200_bank_free(nb200_particle_soa* particles) {
       cudaFree(sh.keys);
     }
     if (sh.has_export) soa_release(sh.exported);
+    for (Replica& r : sh.replicas) cudaFree(r.copy);
   }
   if (bank->mirror.present) {
     nb200_particle_soa& a = bank->mirror.a;

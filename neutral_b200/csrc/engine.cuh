@@ -104,10 +104,16 @@ struct DeviceCtx {
   bool l2_limit_set = false;
   size_t l2_setaside = 0;
   uint64_t launches = 0;
-  // replicas of the caller's read-only inputs (which live on the bank's primary GPU) for the
-  // other GPUs of a single-process multi-GPU bank
-  struct Replica { const void* src; size_t bytes; void* copy; uint64_t generation; };
-  std::vector<Replica> replicas;
+};
+
+// Replica of one of the caller's read-only inputs (which live on the bank's primary GPU) on
+// another GPU of a single-process multi-GPU bank. Owned by the bank's shard: a new bank copies
+// afresh, so an address the caller's allocator hands out twice cannot serve stale contents.
+struct Replica {
+  const void* src;
+  size_t bytes;
+  void* copy;
+  uint64_t generation;
 };
 
 // ------------------------------------------------------------------------------- banks ----
@@ -124,6 +130,7 @@ struct Shard {
   uint64_t pid0 = 0;  // global particle index of origin 0 (the RNG key base)
   SoaView exported{};  // lazily allocated plain SoA view (11 device arrays)
   bool has_export = false;
+  std::vector<Replica> replicas;  // secondary GPUs only
 };
 
 struct StepRequest {  // what solve_transport_2d was asked; pointers on the bank's primary GPU

@@ -87,21 +87,25 @@ __global__ void __launch_bounds__(256) k_stage_tiles(const double* __restrict__ 
   if (lane == 0) fine[tile] = bits_to_double(same ? first : kMixedTileBits);
 }
 
-// One thread per coarse tile: uniform iff its (up to) 4x4 fine tiles are uniform and equal.
+// One warp per coarse tile: uniform iff its (up to) 16x16 fine tiles are uniform and equal.
+// (One thread per coarse tile, 256 dependent loads each in a single CTA, took 55 us.)
 __global__ void __launch_bounds__(256) k_stage_coarse(const double* __restrict__ fine,
                                                       int fine_tx, int fine_ty, int coarse_tx,
                                                       int ncoarse, double* __restrict__ coarse) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (t >= ncoarse) return;
+  const int lane = threadIdx.x & 31;
   constexpr int kRatio = 1 << (kCoarseShift - kTileShift);
   const int fx0 = (t % coarse_tx) * kRatio, fy0 = (t / coarse_tx) * kRatio;
   const unsigned long long first = double_to_bits(fine[fy0 * fine_tx + fx0]);
   bool same = first != kMixedTileBits;
-  for (int j = 0; j < kRatio; ++j)
-    for (int i = 0; i < kRatio; ++i)
-      if (fy0 + j < fine_ty && fx0 + i < fine_tx)
-        same = same && double_to_bits(fine[(fy0 + j) * fine_tx + fx0 + i]) == first;
-  coarse[t] = bits_to_double(same ? first : kMixedTileBits);
+  for (int k = lane; k < kRatio * kRatio; k += 32) {
+    const int j = k / kRatio, i = k % kRatio;
+    if (fy0 + j < fine_ty && fx0 + i < fine_tx)
+      same = same && double_to_bits(fine[(fy0 + j) * fine_tx + fx0 + i]) == first;
+  }
+  same = __all_sync(0xffffffffu, same);
+  if (lane == 0) coarse[t] = bits_to_double(same ? first : kMixedTileBits);
 }
 
 // Rows 0..3 of StepArgs::edges4 (see nb_bank.cuh).
@@ -161,7 +165,7 @@ int launch_stage_tiles(const double* density, int nx, int ny, double* fine, doub
   const int coarse_tx = ((nx - 1) >> kCoarseShift) + 1, coarse_ty = ((ny - 1) >> kCoarseShift) + 1;
   k_stage_tiles<<<blocks_for((size_t)fine_tx * fine_ty * 32, 256), 256, 0, st>>>(
       density, nx, ny, fine_tx, fine_tx * fine_ty, fine);
-  k_stage_coarse<<<blocks_for((size_t)coarse_tx * coarse_ty, 256), 256, 0, st>>>(
+  k_stage_coarse<<<blocks_for((size_t)coarse_tx * coarse_ty * 32, 256), 256, 0, st>>>(
       fine, fine_tx, fine_ty, coarse_tx, coarse_tx * coarse_ty, coarse);
   *map = TileMap{fine, coarse, fine_tx, coarse_tx};
   return 2;
