@@ -190,6 +190,18 @@ __device__ __forceinline__ bool scatter_fast_same_grid(const StepArgs& a, double
 // issues one atomic (north_star phase 5). Off by default: measured, it loses - see DESIGN.md 4.
 template <bool kPreReduce>
 __device__ __forceinline__ void tally_add(double* __restrict__ tally, int cell, double value) {
+#ifdef NB_PROBE_TALLY
+  // Measurement builds (never the product; results are wrong): what does the reduction cost
+  // the event loop? 1: the value is computed and dropped; 2: a plain store instead of the
+  // reduction (same address stream, no read-modify-write at the L2).
+  //   NB200_DEFINES=-DNB_PROBE_TALLY=1 NB200_LIB=libneutral_b200.probe1.so python -m neutral_b200.build
+  if (NB_PROBE_TALLY == 1) {
+    asm volatile("" ::"d"(value), "r"(cell));
+  } else {
+    tally[cell] = value;
+  }
+  return;
+#endif
   if (kPreReduce) {
     const unsigned lane = threadIdx.x & 31;
     const unsigned peers = __match_any_sync(__activemask(), cell);

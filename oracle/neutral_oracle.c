@@ -8,7 +8,7 @@
  * Parity pinning: this port is checked bit-for-bit (every particle field after every
  * timestep, aggregate event counts, tally to 1e-12) against the UNMODIFIED reference
  * omp3/neutral.c compiled from /root/reference (oracle/_ref/libneutral_omp3.so, see
- * oracle/Makefile) by tests/test_oracle_vs_reference.py, against committed golden vectors
+ * oracle/Makefile) by tests/test_oracle.py and tests/test_variants.py, against committed golden vectors
  * generated from that reference build (tests/golden/), and against the Random123
  * known-answer vectors. What it adds over the reference: SoA banks, a global-pid offset
  * (so a shard of the bank replays the same histories) and per-particle event counters.
