@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "engine.cuh"
@@ -71,6 +72,7 @@ TallyGroup* g_mp = nullptr;            // multi-process group of this process (o
 std::vector<TallyGroup*> g_groups;     // every live group (tally-access hooks walk it)
 uint64_t g_replica_generation = 1;     // bumped by nb200_update_replicas
 int g_shard_first = 0, g_shard_count = -1;  // nb200_set_shard
+std::unordered_set<const void*> g_handles;  // every live bank handle (what `Particle*` may be)
 
 // What `validate` reports besides the reference's printed lines.
 struct StepLog {
@@ -386,6 +388,7 @@ Bank* new_bank(int n, uint64_t pid0, int ngpus, int headroom_pct, bool mirror, s
   h->impl = bank;
   h->nviews = nviews;
   bank->header = h;
+  g_handles.insert(views_of(h));
   if (mirror) {
     const size_t m = (size_t)std::max(n, 1);
     nb200_particle_soa& a = bank->mirror.a;
@@ -402,7 +405,8 @@ Bank* new_bank(int n, uint64_t pid0, int ngpus, int headroom_pct, bool mirror, s
 }
 
 Bank* bank_of(nb200_particle_soa* particles) {
-  if (!particles) return nullptr;
+  // only pointers this library handed out are looked behind (the header sits in front of them)
+  if (!particles || !g_handles.count(particles)) return nullptr;
   BankHeader* h = reinterpret_cast<BankHeader*>(particles) - 1;
   if (h->magic != kBankMagic || !h->impl) return nullptr;
   return h->impl;
@@ -1547,7 +1551,16 @@ extern "C" void allocate_host_float_data(float** buf, size_t len) {
   memset(*buf, 0, sizeof(float) * len);
 }
 
-extern "C" void deallocate_data(double* buf) { cudaFree(buf); }
+extern "C" void deallocate_data(double* buf) {
+  // a tally that a sharded run still owes contributions to is completed before it goes away,
+  // and no group keeps pointing at freed memory
+  if (buf) {
+    flush_groups_touching(buf, sizeof(double));
+    for (TallyGroup* g : g_groups)
+      if (g->target == buf) g->target = nullptr;
+  }
+  cudaFree(buf);
+}
 extern "C" void deallocate_host_data(double* buf) { cudaFreeHost(buf); }
 
 extern "C" void copy_buffer(const size_t len, double** src, double** dst, int send) {
@@ -1994,6 +2007,7 @@ extern "C" int nb200_bank_free(nb200_particle_soa* particles) {
   }
   if (g_last_deferred == bank) g_last_deferred = nullptr;
   BankHeader* h = bank->header;
+  g_handles.erase(views_of(h));
   h->magic = 0;
   delete bank;
   free(h);
