@@ -421,14 +421,15 @@ def test_dropin_visit_dump_deck(gpu_lib, port, tmp_path):
     grab = lambda text, key: re.findall(rf"^{key}\s+(\d+)", text, flags=re.M)
     assert grab(out_gpu, "Facets") == grab(out_cpu, "Facets")
     assert grab(out_gpu, "Collisions") == grab(out_cpu, "Collisions")
-    # the particle-density plot of the injected bank: one count per particle in its cell. (The
-    # reference accumulates into an uninitialised malloc, main.c:172, so its own file is only
-    # trustworthy when the allocator happens to hand out zeroed pages: compare with the oracle.)
+    # the particle-density plot of the injected bank: one count per particle in its cell. The
+    # reference accumulates into an UNINITIALISED malloc (main.c:171-172), so a few cells carry
+    # whatever the allocator left there (seen on the GPU box: three denormals, 2.6e-319 ...):
+    # the counts are compared after rounding, against the oracle's injected bank.
     parts = np.fromfile(os.path.join(gpu_dir, "particles1.dat"))
     bank = port.inject(build_problem("visit_small"))
     want = np.bincount(bank.celly.astype(np.int64) * 256 + bank.cellx, minlength=256 * 256)
     assert parts.size == 256 * 256 and parts.sum() == 6000.0
-    assert np.array_equal(parts, want.astype(np.float64))
+    assert np.array_equal(np.rint(parts), want.astype(np.float64))
     for tt in (1, 2, 3):
         a = np.fromfile(os.path.join(gpu_dir, f"energy{tt}.dat"))
         b = np.fromfile(os.path.join(cpu_dir, f"energy{tt}.dat"))
