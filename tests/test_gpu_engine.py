@@ -416,20 +416,22 @@ def test_dropin_visit_dump_deck(gpu_lib, port, tmp_path):
 
     gpu_dir = str(tmp_path / "gpu" / "neutral")
     cpu_dir = str(tmp_path / "cpu" / "neutral")
-    out_gpu = run(DROPIN, RUN_DIR, gpu_dir, {"NB200_HOST_MIRROR": "1"})
-    out_cpu = run(ref_exe, ref_dir, cpu_dir, {"OMP_NUM_THREADS": "4"})
+    out_gpu = run(DROPIN, RUN_DIR, gpu_dir, {"NB200_HOST_MIRROR": "1", "MALLOC_PERTURB_": "255"})
+    out_cpu = run(ref_exe, ref_dir, cpu_dir, {"OMP_NUM_THREADS": "4", "MALLOC_PERTURB_": "255"})
     grab = lambda text, key: re.findall(rf"^{key}\s+(\d+)", text, flags=re.M)
     assert grab(out_gpu, "Facets") == grab(out_cpu, "Facets")
     assert grab(out_gpu, "Collisions") == grab(out_cpu, "Collisions")
     # the particle-density plot of the injected bank: one count per particle in its cell. The
-    # reference accumulates into an UNINITIALISED malloc (main.c:171-172), so a few cells carry
+    # reference accumulates into an UNINITIALISED malloc (main.c:171-172), so cells carry
     # whatever the allocator left there (seen on the GPU box: three denormals, 2.6e-319 ...):
-    # the counts are compared after rounding, against the oracle's injected bank.
+    # both binaries run with glibc's MALLOC_PERTURB_=255, which fills malloc'ed memory with
+    # ~0xff = 0x00, and the counts are compared with the oracle's injected bank.
     parts = np.fromfile(os.path.join(gpu_dir, "particles1.dat"))
     bank = port.inject(build_problem("visit_small"))
     want = np.bincount(bank.celly.astype(np.int64) * 256 + bank.cellx, minlength=256 * 256)
     assert parts.size == 256 * 256 and parts.sum() == 6000.0
-    assert np.array_equal(np.rint(parts), want.astype(np.float64))
+    assert np.array_equal(parts, want.astype(np.float64))
+    assert np.array_equal(parts, np.fromfile(os.path.join(cpu_dir, "particles1.dat")))
     for tt in (1, 2, 3):
         a = np.fromfile(os.path.join(gpu_dir, f"energy{tt}.dat"))
         b = np.fromfile(os.path.join(cpu_dir, f"energy{tt}.dat"))
