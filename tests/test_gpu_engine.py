@@ -431,7 +431,10 @@ def test_dropin_visit_dump_deck(gpu_lib, port, tmp_path):
     want = np.bincount(bank.celly.astype(np.int64) * 256 + bank.cellx, minlength=256 * 256)
     assert parts.size == 256 * 256 and parts.sum() == 6000.0
     assert np.array_equal(parts, want.astype(np.float64))
-    assert np.array_equal(parts, np.fromfile(os.path.join(cpu_dir, "particles1.dat")))
+    for tt in (1, 2, 3, 4):  # ... and after every timestep: the mirror follows the bank
+        a = np.fromfile(os.path.join(gpu_dir, f"particles{tt}.dat"))
+        b = np.fromfile(os.path.join(cpu_dir, f"particles{tt}.dat"))
+        assert a.sum() == 6000.0 and np.array_equal(a, b), tt
     for tt in (1, 2, 3):
         a = np.fromfile(os.path.join(gpu_dir, f"energy{tt}.dat"))
         b = np.fromfile(os.path.join(cpu_dir, f"energy{tt}.dat"))
