@@ -12,7 +12,7 @@ injected bank, ending with the caller-visible tally complete. Prints ONE JSON li
                 timed steps / device time, max over ranks ), inputs resident in HBM;
 * ``e2e``       the same metric with HOST buffers: every step uploads the deck (mesh,
                 cross sections, bank) from pinned host memory, runs the timesteps through
-                solve_transport_2d, and reads tally and bank back (three working sets: the
+                solve_transport_2d, and reads tally and bank back (double-buffered: the
                 copies of neighbouring steps overlap a step's transport);
 * ``roofline``  the history kernel against the ceiling that binds it - the rate at which the
                 L2 retires FP64 reductions, MEASURED IN THIS RUN by the library's microbenchmark
@@ -563,8 +563,8 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
     # ---- e2e: host buffers in, host buffers out, every step ---------------------------
     # Every step uploads ALL of its inputs (mesh, edges, cross-section tables, bank) from
     # pinned host memory and downloads its results (tally, bank) to pinned host memory. The
-    # steps are independent, so the transfers are pipelined the way a production host would:
-    # three device-side working sets; while step i transports on set i%3, the upload of
+    # steps are independent, so the transfers are double-buffered the way a production host
+    # would: two device-side working sets; while step i transports on set i%2, the upload of
     # step i+1 and the download of step i-1 run on their own copy streams. Nothing is skipped:
     # the timed region holds K full uploads, K full runs and K full downloads.
     stage("e2e")
@@ -591,17 +591,9 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
             def field_ptr(self, k):
                 return C.cast(getattr(self.view, k), C.c_void_p).value
 
-        # Three working sets: the upload of step i+1 must not wait for the download of step i-1
-        # out of the same buffers. With two, download + upload of one set (17 + 9 ms at 8 ranks,
-        # more when they share the links: profiles/r02/pcie_probe_all_n8.txt) had to fit between
-        # two transports and did not.
-        sims = [sim]
-        for _ in range(2):
-            extra = Simulation(prob, rank=rank, nranks=world, per_particle_counters=False)
-            extra.load_bank(start_bank)
-            sims.append(extra)
-        sets = [WorkingSet(s) for s in sims]
-        nsets = len(sets)
+        sim_b = Simulation(prob, rank=rank, nranks=world, per_particle_counters=False)
+        sim_b.load_bank(start_bank)
+        sets = [WorkingSet(sim), WorkingSet(sim_b)]
         up, down = torch.cuda.Stream(), torch.cuda.Stream()
         h2d = sum(nbytes(t) for _, t in sets[0].inputs) + sum(nbytes(t) for t in h_bank.values())
         d2h = ncells * 8 + sum(nbytes(t) for t in h_bank.values())
@@ -654,9 +646,9 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
             enqueue_upload(sets[0])
             for i in range(nsteps):
                 if i + 1 < nsteps:
-                    enqueue_upload(sets[(i + 1) % nsets])
-                out += transport(sets[i % nsets])
-                enqueue_download(sets[i % nsets])
+                    enqueue_upload(sets[(i + 1) & 1])
+                out += transport(sets[i & 1])
+                enqueue_download(sets[i & 1])
             up.synchronize()
             down.synchronize()
             return out
@@ -672,7 +664,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
                   {k: round(1e3 * v / (args.steps + min(args.warmup, 2)), 3)
                    for k, v in trace.items()}, file=sys.stderr)
         sampler.window(time.time() - e2e_s, time.time())
-        last = sets[(args.steps - 1) % nsets]
+        last = sets[(args.steps - 1) & 1]
         e2e = {"events": sum(r.events for r in e2e_res), "seconds": e2e_s, "h2d": h2d,
                "hist_ms": sum(r.kernel_ns for r in e2e_res) / 1e6 / args.steps,
                "sort_ms": sum(r.sort_ns for r in e2e_res) / 1e6 / args.steps,
@@ -755,8 +747,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
                                    "--no-e2e --no-decks (dram__bytes_read.sum + "
                                    "dram__bytes_write.sum)"},
         "note": "k_history is bound by L2 FP64 atomics (facets) and FP64/INT issue (collisions), "
-                "not by HBM (DESIGN.md 5); roofline.hbm carries BASELINE.md 5's HBM figure with "
-                "the same keys (bound, achieved, peak, unit, frac, traffic)",
+                "not by HBM (DESIGN.md 5)",
     }
     line = {
         "metric": METRIC, "value": events_all / (elapsed_ms / 1e3), "unit": UNIT,
@@ -790,7 +781,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
                        "history_kernel_ms_per_step": e2e["hist_ms"],
                        "sort_phase_ms_per_step": e2e["sort_ms"],
                        "tally_sum": e2e["tally_sum"], "live_particles_out": e2e_live_all,
-                       "pipeline": "three working sets: upload of step i+1 and download of step "
+                       "pipeline": "double-buffered: upload of step i+1 and download of step "
                                    "i-1 overlap the transport of step i"}
     stage("other decks")
     if world == 1 and not args.no_decks:
