@@ -747,7 +747,8 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
                                    "--no-e2e --no-decks (dram__bytes_read.sum + "
                                    "dram__bytes_write.sum)"},
         "note": "k_history is bound by L2 FP64 atomics (facets) and FP64/INT issue (collisions), "
-                "not by HBM (DESIGN.md 5)",
+                "not by HBM (DESIGN.md 5); roofline.hbm carries BASELINE.md 5's HBM figure with "
+                "the same keys (bound, achieved, peak, unit, frac, traffic)",
     }
     line = {
         "metric": METRIC, "value": events_all / (elapsed_ms / 1e3), "unit": UNIT,
