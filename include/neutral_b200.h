@@ -260,7 +260,9 @@ int nb200_accumulate_clear_async(double* dst_device, double* src_device, size_t 
  * nb200_tally_sync -, which is all the reference's driver needs; 1: every timestep, beside the
  * next timestep's transport; n: every n timesteps);
  * "host_mirror" (see inject_particles); "headroom_pct" (extra bank slots in percent).
- * "tally_prereduce" = 1 implies "fast_div" = 1 (it has no separate IEEE-division build).
+ * "tally_prereduce" = 1 implies "fast_div" = 1 (it has no separate IEEE-division build); it
+ * is an experiment kept for the record (measured slower): its peer mask is the opportunistic
+ * __activemask() pattern, which CUDA does not guarantee to be the converged set.
  * Options are process-wide defaults; nb200_bank_set_option overrides one for one bank (the
  * creation-time options ngpus / host_mirror / headroom_pct / device_inject apply when the bank
  * is created). Returns the previous value, or NB200_BAD_OPTION for an unknown name or a value

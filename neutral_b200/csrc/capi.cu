@@ -2218,6 +2218,10 @@ extern "C" int nb200_mp_connect(const void* blobs) {
   }
   TallyGroup& g = *g_mp;
   const char* all = (const char*)blobs;
+  if (g.collective && getenv("NB200_TEST_IPC_FAIL")) {  // test hook: exercise the host's fallback
+    set_error("nb200_mp_connect: peer mapping refused (NB200_TEST_IPC_FAIL is set)");
+    return -7;
+  }
   if (g.collective) {
     for (int r = 0; r < g.nranks; ++r) {
       if (r == g.mp_rank) continue;
