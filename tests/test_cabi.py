@@ -53,3 +53,33 @@ def test_product_never_touches_the_oracle():
                 hit = re.search(r"import\s+oracle|from\s+oracle|oracle[/.\\]|neutral_oracle|"
                                 r"libneutral_omp3|_ref", text)
                 assert hit is None, (os.path.join(dirpath, f), hit.group(0))
+
+
+def test_options_are_validated_without_a_device(lib):
+    """Option names and ranges are checked on the host (no GPU involved): unknown names and
+    out-of-range values give NB200_BAD_OPTION, legitimate negative values pass."""
+    from neutral_b200.host import NB200_BAD_OPTION
+    assert lib.nb200_set_option(b"no_such_option", 1) == NB200_BAD_OPTION
+    assert b"unknown option" in lib.nb200_last_error()
+    assert lib.nb200_set_option(b"tile_shift", 99) == NB200_BAD_OPTION
+    assert lib.nb200_set_option(b"ngpus", 1000) == NB200_BAD_OPTION
+    assert lib.nb200_get_option(b"no_such_option") == NB200_BAD_OPTION
+    prev = lib.nb200_set_option(b"tile_shift", -1)
+    assert prev != NB200_BAD_OPTION and lib.nb200_get_option(b"tile_shift") == -1
+    assert lib.nb200_set_option(b"tile_shift", prev) == -1
+    for name in (b"tally_reduce_every", b"collective", b"reduce_ctas", b"host_mirror",
+                 b"headroom_pct", b"defer_finish", b"length_bins"):
+        assert lib.nb200_get_option(name) != NB200_BAD_OPTION, name
+
+
+def test_group_entry_points_refuse_without_a_device(lib):
+    import ctypes as C
+    if lib.nb200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    blob = (C.c_char * 256)()
+    assert lib.nb200_mp_init(2, 0, 1024, blob) == -1
+    assert lib.nb200_tally_sync(None) == -1
+    assert lib.nb200_mp_finalize() == 0  # nothing to tear down
+    rate = C.c_double()
+    assert lib.nb200_microbench_red(3, 16 << 20, 10, C.byref(rate)) == -1
+    assert b"no CPU fallback" in lib.nb200_last_error()
