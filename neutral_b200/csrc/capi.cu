@@ -878,11 +878,14 @@ TallyGroup* group_create_local(const Bank* bank, size_t ncells) {
       DeviceGuard guard(g->m[r].dev);
       for (int q = 0; q < g->nranks; ++q) {
         if (q == r) continue;
+        static bool enabled[kMaxDevices][kMaxDevices] = {{false}};  // once per pair and process
+        if (enabled[g->m[r].dev][g->m[q].dev]) continue;
         const cudaError_t err = cudaDeviceEnablePeerAccess(g->m[q].dev, 0);
         if (err != cudaSuccess && err != cudaErrorPeerAccessAlreadyEnabled)
           terminate("cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", g->m[r].dev, g->m[q].dev,
                     cudaGetErrorString(err));
-        (void)cudaGetLastError();
+        if (err != cudaSuccess) (void)cudaGetLastError();  // somebody else had enabled it
+        enabled[g->m[r].dev][g->m[q].dev] = true;
       }
     }
   } else {
