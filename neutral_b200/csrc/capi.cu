@@ -1094,7 +1094,14 @@ const double* replica_of(DeviceCtx& c, Shard& sh, int primary_dev, const double*
       return (const double*)r.copy;
     }
   void* copy = nullptr;
-  CU_FATAL(cudaMalloc(&copy, bytes ? bytes : 8));
+  for (auto& r : sh.replicas)  // a buffer of this size reserved when the bank was created?
+    if (!r.src && r.bytes == bytes) {
+      copy = r.copy;
+      r = sh.replicas.back();
+      sh.replicas.pop_back();
+      break;
+    }
+  if (!copy) CU_FATAL(cudaMalloc(&copy, bytes ? bytes : 8));
   // the primary's uploads went through its own stream: make sure they have landed
   {
     DeviceGuard guard(primary_dev);
@@ -1446,9 +1453,19 @@ extern "C" size_t inject_particles(
       DeviceGuard guard(sh.dev);
       CU_FATAL(cudaStreamSynchronize(ctx_on(sh.dev).stream));
     }
-    // the tally group of a sharded bank (slabs, peer mappings): built here, outside the timesteps
-    if (!single_shard(bank))
+    // the tally group of a sharded bank (slabs, peer mappings) and the buffer its secondary GPUs
+    // will hold their replica of the density mesh in: built here, outside the timesteps
+    if (!single_shard(bank)) {
       bank->group = group_create_local(bank, (size_t)local_nx * (size_t)local_ny);
+      for (Shard& sh : bank->shards) {
+        if (sh.dev == bank->primary_dev) continue;
+        DeviceGuard guard(sh.dev);
+        const size_t bytes = sizeof(double) * (size_t)local_nx * (size_t)local_ny;
+        void* reserved = nullptr;
+        CU_FATAL(cudaMalloc(&reserved, bytes));
+        sh.replicas.push_back({nullptr, bytes, reserved, 0});
+      }
+    }
     refresh_mirror(bank);
     *particles = handle_of(bank);
     return bytes;
