@@ -46,6 +46,7 @@ const OptionSpec kOptionSpecs[] = {
     {"tally_reduce_every", &Options::tally_reduce_every, 0, 1000000},
     {"host_mirror", &Options::host_mirror, 0, 1},
     {"headroom_pct", &Options::headroom_pct, 0, 1000},
+    {"step_graph", &Options::step_graph, 0, 1},
 };
 const int kNumOptionSpecs = (int)(sizeof(kOptionSpecs) / sizeof(kOptionSpecs[0]));
 
@@ -197,6 +198,7 @@ DeviceCtx* ctx_create(int dev) {
     CTX_TRY(cudaEventCreateWithFlags(&c->ev_pub[k], cudaEventDisableTiming));
   }
   CTX_TRY(cudaStreamCreateWithFlags(&c->stage_stream, cudaStreamNonBlocking));
+  CTX_TRY(cudaStreamCreateWithFlags(&c->capture, cudaStreamNonBlocking));
   CTX_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CTX_TRY(cudaEventCreateWithFlags(&c->ev_tiles, cudaEventDisableTiming));
   CTX_TRY(cudaMalloc(&c->d_n_live, sizeof(unsigned)));
@@ -558,8 +560,10 @@ __global__ void k_publish_totals(const unsigned long long* __restrict__ totals,
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&sync->ready), "l"(epoch) : "memory");
 }
 
-// Restages both tables into the device's own block (stage.cu) and fills the views.
-void stage_tables(DeviceCtx& c, StepArgs& a) {
+// Restages both tables into the device's own block (stage.cu) and fills the views. With
+// `reserve_only` nothing is launched: the hints are fetched and the block sized (what has to
+// happen before a timestep is recorded into a graph).
+void stage_tables(DeviceCtx& c, StepArgs& a, bool reserve_only = false) {
   const CsParams ps = table_hint(c, a.s_keys, a.s_n), pa = table_hint(c, a.a_keys, a.a_n);
   auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t kv_s = align(sizeof(double2) * a.s_n), kv_a = align(sizeof(double2) * a.a_n);
@@ -572,15 +576,16 @@ void stage_tables(DeviceCtx& c, StepArgs& a) {
     CU_FATAL(cudaMalloc(&c.d_cs_stage, need));
     c.cs_stage_bytes = need;
   }
+  if (reserve_only) return;
   char* p = c.d_cs_stage;
   double2* d_kv_s = (double2*)p; p += kv_s;
   double2* d_kv_a = (double2*)p; p += kv_a;
   int* d_bk_s = (int*)p; p += bk_s;
   int* d_bk_a = (int*)p;
   c.launches += launch_stage_cs(a.s_keys, a.s_vals, a.s_n, d_kv_s, d_bk_s, ps.bits0, ps.shift,
-                                ps.nb, a.same_keys ? a.a_keys : nullptr, a.totals, c.stream);
+                                ps.nb, a.same_keys ? a.a_keys : nullptr, a.totals, c.work);
   c.launches += launch_stage_cs(a.a_keys, a.a_vals, a.a_n, d_kv_a, d_bk_a, pa.bits0, pa.shift,
-                                pa.nb, nullptr, a.totals, c.stream);
+                                pa.nb, nullptr, a.totals, c.work);
   a.cs_s = CsStage{d_kv_s, d_bk_s, ps.bits0, ps.shift, ps.nb, a.s_n};
   a.cs_a = CsStage{d_kv_a, d_bk_a, pa.bits0, pa.shift, pa.nb, a.a_n};
 }
@@ -668,8 +673,42 @@ struct ShardIO {
 };
 
 // Enqueues one timestep of one shard on its device's stream (the device is current).
-void enqueue_shard_step(DeviceCtx& c, const Bank* bank, Shard& sh, const StepRequest& rq,
-                        const ShardIO& io, int slot, SyncBlock* sync, unsigned long long epoch) {
+// An event the host will wait on or read a time from. While a timestep is being recorded into
+// a graph it has to become an event-record NODE (cudaEventRecordExternal); a plain record
+// inside a capture is only an edge between the captured streams.
+void record_external(DeviceCtx& c, cudaEvent_t ev) {
+  if (c.work == c.capture)
+    CU_FATAL(cudaEventRecordWithFlags(ev, c.work, cudaEventRecordExternal));
+  else
+    CU_FATAL(cudaEventRecord(ev, c.work));
+}
+
+// Everything a timestep of this shard may have to allocate or read back (hints), done ahead of
+// the timestep's own calls - nothing of this kind may happen while a graph is being recorded.
+void prepare_shard_step(DeviceCtx& c, const Bank* bank, Shard& sh, const StepRequest& rq,
+                        const ShardIO& io) {
+  if (!opt_of(bank, &Options::pipeline)) return;
+  double w, h;
+  mesh_hint(c, io.edgex, io.edgey, rq.nx, rq.ny, &w, &h);
+  StepArgs a{};
+  a.s_keys = io.s_keys;
+  a.s_n = rq.s_n;
+  a.a_keys = io.a_keys;
+  a.a_n = rq.a_n;
+  stage_tables(c, a, true);
+  int shift = opt_of(bank, &Options::tile_shift), tx = 1, nt = 1;
+  const long long nbins = sort_key_space(rq.nx, rq.ny, opt_of(bank, &Options::length_bins), &shift,
+                                         &tx, &nt);
+  reserve_mesh_scratch(c, rq.nx, rq.ny, nbins);
+  if (!sh.has_alt) {
+    bank_alloc(c, sh.alt, sh.capacity);
+    device_zalloc(c, &sh.keys, (size_t)sh.capacity);
+    sh.has_alt = true;
+  }
+}
+
+void record_shard_step(DeviceCtx& c, const Bank* bank, Shard& sh, const StepRequest& rq,
+                       const ShardIO& io, int slot, SyncBlock* sync, unsigned long long epoch) {
   StepArgs a{};
   a.nx = rq.nx;
   a.ny = rq.ny;
@@ -697,8 +736,8 @@ void enqueue_shard_step(DeviceCtx& c, const Bank* bank, Shard& sh, const StepReq
   a.logt = c.d_logt;
 
   const int opt_l2 = opt_of(bank, &Options::l2_persist);
-  CU_FATAL(cudaMemsetAsync(c.d_totals, 0, sizeof(unsigned long long) * kTotCount, c.stream));
-  CU_FATAL(cudaEventRecord(c.ev_begin[slot], c.stream));
+  CU_FATAL(cudaMemsetAsync(c.d_totals, 0, sizeof(unsigned long long) * kTotCount, c.work));
+  record_external(c, c.ev_begin[slot]);
   if (opt_of(bank, &Options::pipeline)) {
     double mesh_w = 1.0, mesh_h = 1.0;
     mesh_hint(c, io.edgex, io.edgey, rq.nx, rq.ny, &mesh_w, &mesh_h);
@@ -716,13 +755,13 @@ void enqueue_shard_step(DeviceCtx& c, const Bank* bank, Shard& sh, const StepReq
     // P0: restage the read-only inputs (cross-section tables, density tile map)
     const bool overlap = opt_of(bank, &Options::stage_overlap) != 0;
     if (overlap) {
-      CU_FATAL(cudaEventRecord(c.ev_fork, c.stream));
+      CU_FATAL(cudaEventRecord(c.ev_fork, c.work));
       CU_FATAL(cudaStreamWaitEvent(c.stage_stream, c.ev_fork, 0));
       stage_tiles(c, a, c.stage_stream);
       CU_FATAL(cudaEventRecord(c.ev_tiles, c.stage_stream));
     }
     stage_tables(c, a);
-    if (!overlap) stage_tiles(c, a, c.stream);
+    if (!overlap) stage_tiles(c, a, c.work);
     // P1-P3: begin-step set-up, classification and counting sort into the double buffer
     SortArgs s{};
     s.nq = std::max(opt_of(bank, &Options::length_bins), 1);
@@ -744,13 +783,13 @@ void enqueue_shard_step(DeviceCtx& c, const Bank* bank, Shard& sh, const StepReq
     s.bin_cursor = c.d_bins + s.nbins;
     s.chunk_sum = c.d_bins + 2 * (size_t)s.nbins;
     s.n_live = c.d_n_live;
-    c.launches += launch_sort_phase(a, s, sh.alt, c.stream);
+    c.launches += launch_sort_phase(a, s, sh.alt, c.work);
     if (s.n_upper > 0) {  // the sort ran: the double buffer now holds the bank
       std::swap(sh.cur, sh.alt);
       a.bank = sh.cur;
     }
-    if (overlap) CU_FATAL(cudaStreamWaitEvent(c.stream, c.ev_tiles, 0));
-    CU_FATAL(cudaEventRecord(c.ev_mid[slot], c.stream));
+    if (overlap) CU_FATAL(cudaStreamWaitEvent(c.work, c.ev_tiles, 0));
+    record_external(c, c.ev_mid[slot]);
     // P4: event loop over the sorted live prefix
     const bool fast_div = opt_of(bank, &Options::fast_div) != 0;
     c.launches += launch_history(a, c.d_n_live, s.n_upper, fast_div,
@@ -760,19 +799,62 @@ void enqueue_shard_step(DeviceCtx& c, const Bank* bank, Shard& sh, const StepReq
                                  opt_l2 == 2 ? sizeof(double) * (size_t)rq.nx * rq.ny
                                              : c.cs_stage_bytes,
                                  opt_l2 == 2 ? c.l2_setaside : 0,
-                                 opt_of(bank, &Options::history_smem_pad), c.stream);
+                                 opt_of(bank, &Options::history_smem_pad), c.work);
   } else {
     if (a.same_keys)
-      c.launches += launch_compare_grids(a.s_keys, a.a_keys, a.s_n, a.totals, c.stream);
-    CU_FATAL(cudaEventRecord(c.ev_mid[slot], c.stream));
-    c.launches += launch_history_direct(a, c.stream);
+      c.launches += launch_compare_grids(a.s_keys, a.a_keys, a.s_n, a.totals, c.work);
+    record_external(c, c.ev_mid[slot]);
+    c.launches += launch_history_direct(a, c.work);
   }
   CU_FATAL(cudaGetLastError());
-  CU_FATAL(cudaEventRecord(c.ev_end[slot], c.stream));
-  k_publish_totals<<<1, 32, 0, c.stream>>>(c.d_totals, c.h_totals_dev + (size_t)slot * kTotCount,
+  record_external(c, c.ev_end[slot]);
+  k_publish_totals<<<1, 32, 0, c.work>>>(c.d_totals, c.h_totals_dev + (size_t)slot * kTotCount,
                                            sync, epoch);
-  CU_FATAL(cudaEventRecord(c.ev_pub[slot], c.stream));
+  record_external(c, c.ev_pub[slot]);
   c.launches += 1;
+}
+
+// Enqueues one timestep of one shard on its device's stream (the device is current): call by
+// call, or - option step_graph - recorded into a graph on the capture stream, which then
+// updates the device's executable graph in place (same topology every timestep; only the
+// parameters move) and goes out as ONE launch. A topology change (an option flipped, an empty
+// bank) re-instantiates.
+void enqueue_shard_step(DeviceCtx& c, const Bank* bank, Shard& sh, const StepRequest& rq,
+                        const ShardIO& io, int slot, SyncBlock* sync, unsigned long long epoch) {
+  prepare_shard_step(c, bank, sh, rq, io);
+  const bool graph = opt_of(bank, &Options::step_graph) && opt_of(bank, &Options::pipeline) &&
+                     !opt_of(bank, &Options::l2_persist) &&
+                     !opt_of(bank, &Options::history_smem_pad);
+  if (!graph) {
+    c.work = c.stream;
+    record_shard_step(c, bank, sh, rq, io, slot, sync, epoch);
+    c.pending_steps++;
+    return;
+  }
+  CU_FATAL(cudaStreamBeginCapture(c.capture, cudaStreamCaptureModeRelaxed));
+  c.work = c.capture;
+  record_shard_step(c, bank, sh, rq, io, slot, sync, epoch);
+  c.work = c.stream;
+  cudaGraph_t recorded = nullptr;
+  CU_FATAL(cudaStreamEndCapture(c.capture, &recorded));
+  bool fresh = c.step_exec == nullptr;
+  if (!fresh) {
+    cudaGraphExecUpdateResultInfo info{};
+    if (cudaGraphExecUpdate(c.step_exec, recorded, &info) != cudaSuccess) {
+      (void)cudaGetLastError();
+      cudaGraphExecDestroy(c.step_exec);
+      c.step_exec = nullptr;
+      fresh = true;
+    } else {
+      c.graph_updates++;
+    }
+  }
+  if (fresh) {
+    CU_FATAL(cudaGraphInstantiate(&c.step_exec, recorded, 0));
+    c.graph_instantiations++;
+  }
+  CU_FATAL(cudaGraphDestroy(recorded));
+  CU_FATAL(cudaGraphLaunch(c.step_exec, c.stream));
   c.pending_steps++;
 }
 

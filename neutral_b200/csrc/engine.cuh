@@ -50,6 +50,7 @@ struct Options {
   int tally_reduce_every = 0;  // timesteps between reduce-scatters of a sharded tally; 0: on demand
   int host_mirror = 0;   // keep a host copy of the bank behind the handle's 11 pointers
   int headroom_pct = 0;  // extra bank capacity for produced particles (omp3/neutral.c:570: 100)
+  int step_graph = 0;    // submit a timestep as one CUDA graph launch instead of ~23 driver calls
 };
 
 struct OptionSpec {
@@ -72,6 +73,13 @@ struct DeviceCtx {
   cudaStream_t stream = 0;  // every kernel of this device's banks (nb200_set_stream)
   cudaStream_t stage_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_tiles = nullptr;
+  // option step_graph: a timestep's kernels are recorded on `capture` (never executed there),
+  // the executable graph is updated in place with the step's parameters and launched on
+  // `stream`. `work` is where the step's calls go: `stream`, or `capture` while recording.
+  cudaStream_t capture = nullptr;
+  cudaStream_t work = 0;
+  cudaGraphExec_t step_exec = nullptr;
+  uint64_t graph_updates = 0, graph_instantiations = 0;
   LogTable* d_logt = nullptr;
   SinCosTable* d_sct = nullptr;
   unsigned long long* d_totals = nullptr;
