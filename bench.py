@@ -241,7 +241,7 @@ def run_reference_arm(args, rank: int, world: int):
     from neutral_b200.decks import load_deck
     deck = load_deck(args.deck)
     nglobal = global_particles(deck, args, max(world, args.gpus, 1))
-    budget = float(os.environ.get("NB200_REF_BUDGET_S", "900"))
+    budget = float(os.environ.get("NB200_REF_BUDGET_S", "600"))
     res = reference_rate(args.deck, nglobal, budget, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT,

@@ -260,6 +260,12 @@ int nb200_accumulate_clear_async(double* dst_device, double* src_device, size_t 
  * nb200_tally_sync -, which is all the reference's driver needs; 1: every timestep, beside the
  * next timestep's transport; n: every n timesteps);
  * "host_mirror" (see inject_particles); "headroom_pct" (extra bank slots in percent).
+ * "step_graph" (1, default: the timestep's kernels, memsets and event records are recorded
+ * on a capture stream of the library's own, the device's executable CUDA graph is updated in
+ * place with the step's parameters and submitted as ONE launch on the library's stream - same
+ * kernels, same order, same results; 0: the ~23 driver calls are issued one by one. The
+ * occupancy / L2 probes "history_smem_pad", "l2_persist" and "pipeline" = 0 always take the
+ * call-by-call path).
  * "tally_prereduce" = 1 implies "fast_div" = 1 (it has no separate IEEE-division build); it
  * is an experiment kept for the record (measured slower): its peer mask is the opportunistic
  * __activemask() pattern, which CUDA does not guarantee to be the converged set.

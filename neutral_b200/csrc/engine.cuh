@@ -50,7 +50,7 @@ struct Options {
   int tally_reduce_every = 0;  // timesteps between reduce-scatters of a sharded tally; 0: on demand
   int host_mirror = 0;   // keep a host copy of the bank behind the handle's 11 pointers
   int headroom_pct = 0;  // extra bank capacity for produced particles (omp3/neutral.c:570: 100)
-  int step_graph = 0;    // submit a timestep as one CUDA graph launch instead of ~23 driver calls
+  int step_graph = 1;    // submit a timestep as one CUDA graph launch instead of ~23 driver calls
 };
 
 struct OptionSpec {

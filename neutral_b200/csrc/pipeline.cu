@@ -84,9 +84,23 @@ __global__ void __launch_bounds__(256) k_begin_step(const StepArgs a, const Sort
       const double d_facet = x_facet ? (gx * v) * uxi : (gy * v) * uyi;
       const double d_coll = mfp * cell_mfp;
       const double d_census = v * a.dt;
-      const int cls = (d_coll < d_facet && d_coll < d_census) ? kClsCollision
-                      : (d_facet < d_census)                  ? kClsFacet
-                                                              : kClsCensus;
+      // The class is the kind of work the history is about to do, which is the first event's
+      // kind except for a particle of a dense cell that happens to sit next to a cell edge: its
+      // first event is a facet, the ~1000 collisions of a collider follow (the path sample
+      // carries over into the next cell, :282). Sorted among the streamers it would hold a
+      // warp of finished lanes for a collider's lifetime - the split deck's launch ended with
+      // 1.2 ms of a dozen such warps (profiles/r02/warp_trace_r2b_split.txt). It is a collider
+      // when the sampled collision lies inside this timestep and less than ~8 cells ahead.
+      const float cells_per_length =
+          fabsf((float)dir.x) * s.inv_dx + fabsf((float)dir.y) * s.inv_dy;
+#ifdef NB_CLASS_FIRST_EVENT_ONLY  // A/B build: round 1's rule (the first event's kind)
+      const bool collides_soon = false;
+#else
+      const bool collides_soon = d_coll < d_census && (float)d_coll * cells_per_length < 8.0f;
+#endif
+      const int cls = ((d_coll < d_facet && d_coll < d_census) || collides_soon) ? kClsCollision
+                      : (d_facet < d_census)                                     ? kClsFacet
+                                                                                 : kClsCensus;
       const unsigned tile = s.tile_shift >= 0
                                 ? (unsigned)((cy >> s.tile_shift) * s.tiles_x + (cx >> s.tile_shift))
                                 : 0u;
@@ -99,8 +113,7 @@ __global__ void __launch_bounds__(256) k_begin_step(const StepArgs a, const Sort
       if (s.nq > 1) {
         float est = 1.0f;
         if (cls == kClsFacet)
-          est += (fabsf((float)dir.x) * s.inv_dx + fabsf((float)dir.y) * s.inv_dy) *
-                 (float)v * (float)a.dt;
+          est += cells_per_length * (float)v * (float)a.dt;
         else if (cls == kClsCollision)
           est += 101.0f * __logf(fmaxf((float)e, 1.0f));
         const int q = (int)(__log2f(est) * s.q_scale);

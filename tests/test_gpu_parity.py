@@ -37,13 +37,14 @@ MODES = {
     "pipeline-prereduce": dict(pipeline=1, fast_div=1, tile_shift=9, length_bins=512,
                                tally_prereduce=1),
     "direct": dict(pipeline=0, fast_div=0, tile_shift=9, length_bins=512),
-    # the timestep recorded into a CUDA graph and submitted as one launch
-    "pipeline-graph": dict(pipeline=1, fast_div=1, tile_shift=8, length_bins=512, step_graph=1),
+    # the timestep's ~23 driver calls issued one by one instead of recorded into a CUDA graph
+    # and submitted as one launch (the default since round 2)
+    "pipeline-calls": dict(pipeline=1, fast_div=1, tile_shift=8, length_bins=512, step_graph=0),
 }
 
 
 DEFAULTS = dict(MODES["pipeline"], tally_prereduce=0, stage_overlap=1, history_smem_pad=0,
-                step_graph=0)
+                step_graph=1)
 
 
 @pytest.fixture(params=list(MODES))
