@@ -615,7 +615,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
                 trace[name] = trace.get(name, 0.0) + time.perf_counter() - t0
             return time.perf_counter()
 
-        def transport(ws):
+        def transport(ws, once_fed=None):
             t = time.perf_counter()
             torch.cuda.current_stream().wait_event(ws.uploaded)
             if trace is not None:
@@ -624,7 +624,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
             _check(lib.nb200_bank_import(ws.sim.bank), "bank_import")
             ws.sim.tally.zero()
             t = lap("import+zero (enqueue)", t)
-            out = ws.sim.run_pipelined()
+            out = ws.sim.run_pipelined(once_fed=once_fed)
             t = lap("timesteps", t)
             if world > 1:
                 ws.sim.tally_sync()
@@ -642,13 +642,20 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
             ws.downloaded.record(down)
 
         def e2e_run(nsteps):
+            # The ~30 copy calls of a step (download of the previous run's results, upload of
+            # the next run's inputs) are issued once the GPU has this run's first timesteps
+            # queued, not in the gap between two runs where it would sit idle behind them.
             out = []
             enqueue_upload(sets[0])
             for i in range(nsteps):
-                if i + 1 < nsteps:
-                    enqueue_upload(sets[(i + 1) & 1])
-                out += transport(sets[i & 1])
-                enqueue_download(sets[i & 1])
+                def copies_of_the_neighbours(i=i):
+                    if i > 0:
+                        enqueue_download(sets[(i - 1) & 1])
+                    if i + 1 < nsteps:
+                        enqueue_upload(sets[(i + 1) & 1])
+                out += transport(sets[i & 1], copies_of_the_neighbours)
+            if nsteps > 0:
+                enqueue_download(sets[(nsteps - 1) & 1])
             up.synchronize()
             down.synchronize()
             return out

@@ -340,17 +340,23 @@ class Simulation:
         return [self.step(tt) for tt in range(1, n + 1)]
 
     def run_pipelined(self, iterations: Optional[int] = None, first_tt: int = 1,
-                      depth: int = 3) -> List[StepResult]:
+                      depth: int = 3, once_fed=None) -> List[StepResult]:
         """The same timesteps without a host round trip between them: up to ``depth`` steps
         are enqueued (``defer_finish``) before the oldest is collected, so the GPU goes from
         one timestep's history kernel straight into the next one's sort. Results are those of
-        :meth:`run` (the steps execute in stream order either way)."""
+        :meth:`run` (the steps execute in stream order either way). ``once_fed`` (optional
+        callable) runs once, as soon as the GPU has ``depth`` timesteps queued: the place for
+        host work that should not sit between two deck runs (enqueueing copies of other
+        working sets)."""
         n = self.problem.deck.iterations if iterations is None else iterations
         out: List[StepResult] = []
         inflight = 0
         for tt in range(first_tt, first_tt + n):
             self.step(tt, defer=True)
             inflight += 1
+            if once_fed is not None and (inflight >= depth or tt == first_tt + n - 1):
+                once_fed()
+                once_fed = None
             if inflight >= depth:
                 out.append(self.step_finish())
                 inflight -= 1
