@@ -672,7 +672,6 @@ struct ShardIO {
   uint64_t *r0, *r1, *r2;
 };
 
-// Enqueues one timestep of one shard on its device's stream (the device is current).
 // An event the host will wait on or read a time from. While a timestep is being recorded into
 // a graph it has to become an event-record NODE (cudaEventRecordExternal); a plain record
 // inside a capture is only an edge between the captured streams.
@@ -707,6 +706,8 @@ void prepare_shard_step(DeviceCtx& c, const Bank* bank, Shard& sh, const StepReq
   }
 }
 
+// The calls of one timestep of one shard, issued on c.work (the device is current): the
+// device's stream, or its capture stream while the timestep is being recorded into a graph.
 void record_shard_step(DeviceCtx& c, const Bank* bank, Shard& sh, const StepRequest& rq,
                        const ShardIO& io, int slot, SyncBlock* sync, unsigned long long epoch) {
   StepArgs a{};
