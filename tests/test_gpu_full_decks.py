@@ -5,7 +5,7 @@ the UNMODIFIED reference omp3 build printed for the same decks (SURVEY.md 2.2 / 
 measured with the reference binary, `Facets` / `Collisions` / `Particles` lines of
 main.c:118-125 and omp3/neutral.c:205) - exact; (ii) the reference's own golden tally sums of
 problems/neutral.tests through `validate`'s 1e-3 criterion (omp3/neutral.c:549) and the tally
-sums the reference build produced, to 1e-9; (iii) size-independent invariants: every processed
+sums the reference build produced, to 1e-10; (iii) size-independent invariants: every processed
 particle ends the step in exactly one census or death, dead particles are never processed
 again, the tally only grows."""
 import numpy as np
@@ -50,7 +50,7 @@ def test_full_deck_matches_the_reference_run(gpu_lib, deck):
     assert np.all(tally >= 0.0)
     got = float(np.sum(tally))
     assert got > 0.0
-    assert abs(got - tally_sum) <= 1e-9 * tally_sum
+    assert abs(got - tally_sum) <= 1e-10 * tally_sum
     if deck in NEUTRAL_TESTS:  # validate()'s criterion, omp3/neutral.c:549
         assert abs(got - NEUTRAL_TESTS[deck]) / NEUTRAL_TESTS[deck] < 1e-3
     bank = sim.bank_to_host()
@@ -94,7 +94,7 @@ def test_full_deck_bank_is_bit_identical_to_the_reference(gpu_lib, deck):
     """Full-size parity against fixtures generated from the UNMODIFIED reference library
     (tests/golden/make_golden_full.py): per-timestep counts exact, the injected bank and the
     final bank bit-identical in all 11 fields (sha256 per field, 1e6 / 1e7 particles), the tally
-    through its total and a 64 x 64 block-sum image (1e-9: atomic summation order)."""
+    through its total and a 64 x 64 block-sum image (1e-10: atomic summation order; observed 1e-15)."""
     import hashlib
 
     from neutral_b200.bank import ALL_FIELDS
@@ -123,13 +123,13 @@ def test_full_deck_bank_is_bit_identical_to_the_reference(gpu_lib, deck):
     assert hashes(bank) == g["final_hashes"]
     assert int(np.count_nonzero(bank.dead == 0)) == g["live"]
     tally = sim.tally_to_host()
-    assert abs(float(tally.sum()) - g["tally_sum"]) <= 1e-9 * g["tally_sum"]
+    assert abs(float(tally.sum()) - g["tally_sum"]) <= 1e-10 * g["tally_sum"]
     blocks = 64
     by, bx = d.ny // blocks, d.nx // blocks
     img = tally.reshape(d.ny, d.nx)[:by * blocks, :bx * blocks] \
         .reshape(blocks, by, blocks, bx).sum(axis=(1, 3)).ravel()
     want = np.array(g["tally_block_sums"])
-    assert np.all(np.abs(img - want) <= 1e-9 * np.maximum(np.abs(img), np.abs(want)))
+    assert np.all(np.abs(img - want) <= 1e-10 * np.maximum(np.abs(img), np.abs(want)))
     sim.free()
 
 
