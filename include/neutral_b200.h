@@ -260,6 +260,10 @@ int nb200_accumulate_clear_async(double* dst_device, double* src_device, size_t 
  * nb200_tally_sync -, which is all the reference's driver needs; 1: every timestep, beside the
  * next timestep's transport; n: every n timesteps);
  * "host_mirror" (see inject_particles); "headroom_pct" (extra bank slots in percent).
+ * "stagger_at" / "stagger_share" / "stagger_min" (an experiment kept for the record, off: when
+ * the collision class is at least stagger_min per mille of the live bank and fits the first wave
+ * of CTAs, stagger_share percent of its CTAs are dispatched behind the first stagger_at percent
+ * of the streamer CTAs; measured slower than class order).
  * "step_graph" (1, default: the timestep's kernels, memsets and event records are recorded
  * on a capture stream of the library's own, the device's executable CUDA graph is updated in
  * place with the step's parameters and submitted as ONE launch on the library's stream - same

@@ -47,6 +47,9 @@ const OptionSpec kOptionSpecs[] = {
     {"host_mirror", &Options::host_mirror, 0, 1},
     {"headroom_pct", &Options::headroom_pct, 0, 1000},
     {"step_graph", &Options::step_graph, 0, 1},
+    {"stagger_at", &Options::stagger_at, 0, 95},
+    {"stagger_share", &Options::stagger_share, 0, 100},
+    {"stagger_min", &Options::stagger_min, 0, 1000},
 };
 const int kNumOptionSpecs = (int)(sizeof(kOptionSpecs) / sizeof(kOptionSpecs[0]));
 
@@ -201,7 +204,8 @@ DeviceCtx* ctx_create(int dev) {
   CTX_TRY(cudaStreamCreateWithFlags(&c->capture, cudaStreamNonBlocking));
   CTX_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CTX_TRY(cudaEventCreateWithFlags(&c->ev_tiles, cudaEventDisableTiming));
-  CTX_TRY(cudaMalloc(&c->d_n_live, sizeof(unsigned)));
+  CTX_TRY(cudaMalloc(&c->d_n_live, 2 * sizeof(unsigned)));
+  CTX_TRY(cudaMemset(c->d_n_live, 0, 2 * sizeof(unsigned)));
 #undef CTX_TRY
   return c;
 }
@@ -792,6 +796,9 @@ void record_shard_step(DeviceCtx& c, const Bank* bank, Shard& sh, const StepRequ
     if (overlap) CU_FATAL(cudaStreamWaitEvent(c.work, c.ev_tiles, 0));
     record_external(c, c.ev_mid[slot]);
     // P4: event loop over the sorted live prefix
+    a.stagger_at = opt_of(bank, &Options::stagger_at);
+    a.stagger_share = opt_of(bank, &Options::stagger_share);
+    a.stagger_min = opt_of(bank, &Options::stagger_min);
     const bool fast_div = opt_of(bank, &Options::fast_div) != 0;
     c.launches += launch_history(a, c.d_n_live, s.n_upper, fast_div,
                                  opt_of(bank, &Options::tally_prereduce) != 0,

@@ -50,6 +50,9 @@ struct Options {
   int tally_reduce_every = 0;  // timesteps between reduce-scatters of a sharded tally; 0: on demand
   int host_mirror = 0;   // keep a host copy of the bank behind the handle's 11 pointers
   int headroom_pct = 0;  // extra bank capacity for produced particles (omp3/neutral.c:570: 100)
+  int stagger_at = 0;      // percent of the streamer CTAs dispatched in front of the delayed colliders
+  int stagger_share = 50;  // percent of the collider CTAs that are delayed
+  int stagger_min = 35;    // colliders' share of the live bank (per mille) from which on it is done
   int step_graph = 1;    // submit a timestep as one CUDA graph launch instead of ~23 driver calls
 };
 

@@ -55,6 +55,8 @@ struct Parked {
   double edep[kHistoryThreads];
   int origin[kHistoryThreads];  // index in injection order: RNG key and counter slot
   unsigned nc[kHistoryThreads];  // collisions so far this step = the RNG counter state
+  int slot[kHistoryThreads];     // the thread's slot of the bank (dispatch_group is not the
+                                 // identity any more: parked, or the event loop spills for it)
 };
 
 #ifdef NB_HISTORY_MAXNREG  // experiments: cap the registers directly instead of through min blocks
@@ -77,6 +79,34 @@ __device__ __forceinline__ unsigned long long trace_now() {
 }
 #endif
 
+// Which 128-slot group of the sorted bank the CTA with this index works on. CTAs are dispatched
+// in index order, and the sorted bank has the collision class in front: all its warps start at
+// once and hold their slots for the ~1000 dependent collisions of a collider (2.3 ms on csp),
+// latency-bound and unimpressed by their neighbours, while the streamers beside them get
+// what is left of the issue slots - and then have the SMs to themselves, bound by the L2's
+// reduction rate with issue slots to spare (profiles/r02/warp_trace_r2b_csp_step*.txt). The
+// streamers' rate is a concave function of the colliders resident beside them, so the same
+// collider residency spread over the launch costs them less: when the colliders are a
+// sizeable share of the bank but fit the first wave, `stagger_share` percent of their CTAs go
+// out behind the first `stagger_at` percent of the streamer CTAs instead of in front. A
+// permutation of whole groups inside the live prefix; no history changes.
+__device__ __forceinline__ unsigned dispatch_group(const StepArgs& a, unsigned b, unsigned n_live,
+                                                   unsigned n_coll) {
+  if (a.stagger_at <= 0) return b;
+  const unsigned T = n_live / kHistoryThreads;   // full groups of the live prefix
+  const unsigned NC = n_coll / kHistoryThreads;  // groups of colliders only
+  if (b >= T || NC >= T || NC > 148u * NB_HISTORY_MIN_BLOCKS ||
+      (unsigned long long)n_coll * 1000ull < (unsigned long long)a.stagger_min * n_live)
+    return b;
+  const unsigned nB = NC * (unsigned)a.stagger_share / 100u;  // delayed collider groups
+  const unsigned A = NC - nB;
+  const unsigned P = A + (unsigned)(((unsigned long long)(T - NC) * (unsigned)a.stagger_at) / 100ull);
+  if (b < A) return b;                  // the colliders that start with the launch
+  if (b < P) return NC + (b - A);       // the first streamers
+  if (b < P + nB) return A + (b - P);   // the delayed colliders
+  return b;                             // the remaining streamers: NC + (P - A) + (b - P - nB)
+}
+
 template <bool kFastDiv, bool kPreReduce>
 __global__ void NB_HISTORY_BOUNDS
 k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
@@ -85,26 +115,31 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
 #define PARKED(name) park.name[threadIdx.x]
 #else
   double park_e, park_Sig_s, park_p_absorb, park_rho, park_edep;
-  int park_origin;
+  int park_origin, park_slot;
   unsigned park_nc;
 #define PARKED(name) park_##name
 #endif
-  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned live = n_live[0];
   unsigned nf = 0, census = 0, processed = 0, died = 0;
   PARKED(nc) = 0;
+  PARKED(slot) = (int)(dispatch_group(a, blockIdx.x, live, n_live[1]) * blockDim.x + threadIdx.x);
 #ifdef NB_TRACE_WARPS
   const unsigned long long trace_t0 = trace_now();
 #endif
 
   int4 m = make_int4(0, 0, 1, 0);
-  if (slot < (int)*n_live) m = a.bank.meta[slot];
+  if (PARKED(slot) < (int)live) m = a.bank.meta[PARKED(slot)];
 
   if (!m.z) {
     processed = 1;
-    const double2 pos = a.bank.pos[slot];
-    const double2 dir = a.bank.dir[slot];
-    const double2 ew = a.bank.ew[slot];
-    const double2 tm = a.bank.tm[slot];  // k_begin_step left (dt, first path sample) here
+    double2 pos, dir, ew, tm;
+    {
+      const int slot = PARKED(slot);
+      pos = a.bank.pos[slot];
+      dir = a.bank.dir[slot];
+      ew = a.bank.ew[slot];
+      tm = a.bank.tm[slot];  // k_begin_step left (dt, first path sample) here
+    }
     double x = pos.x, y = pos.y, ox = dir.x, oy = dir.y, w = ew.y;
     double dtc = tm.x, mfp = tm.y;
     int cx = m.x, cy = m.y;
@@ -365,6 +400,7 @@ k_history(const StepArgs a, const unsigned* __restrict__ n_live) {
     }
 
     died = (flags & kFlagDead) ? 1u : 0u;
+    const int slot = PARKED(slot);
     a.bank.pos[slot] = make_double2(x, y);
     a.bank.dir[slot] = make_double2(ox, oy);
     a.bank.ew[slot] = make_double2(PARKED(e), w);

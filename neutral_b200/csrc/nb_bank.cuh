@@ -127,6 +127,11 @@ struct StepArgs {
   // the per-facet correction.
   const double* edges4;
   int edge_stride;
+  // Staggered dispatch of the collision class (history.cu: dispatch_group): percent of the
+  // streamer CTAs that go out in front of the delayed colliders (0: class order), percent of
+  // the collider CTAs that are delayed, and the colliders' share of the live bank (per mille)
+  // from which on it is done.
+  int stagger_at, stagger_share, stagger_min;
 };
 
 // Scratch of the per-step counting sort (pipeline.cu).
@@ -135,7 +140,8 @@ struct SortArgs {
   unsigned* bin_count;   // [nbins] histogram
   unsigned* bin_cursor;  // [nbins] running destination of every bin
   unsigned* chunk_sum;   // [ceil(nbins / 2048)] scratch of the histogram scan
-  unsigned* n_live;      // device scalar: slots in front of the dead bin after the sort
+  unsigned* n_live;      // device scalars: [0] slots in front of the dead bin after the sort,
+                         // [1] slots of the collision class (the front of the sorted bank)
   int nbins;             // 3 classes x nq length bins x ntiles + 1 dead bin
   int nq;                // bins of expected history length (1: none)
   float q_scale;         // length bins per octave

@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_bins(SortArgs s, const un
   for (int k = 0; k < kScanItems; ++k) {
     if (base + k < s.nbins) {
       s.bin_cursor[base + k] = run;
-      if (base + k == s.nbins - 1) *s.n_live = run;
+      if (base + k == s.nbins - 1) s.n_live[0] = run;
+      if (base + k == s.nq * s.ntiles) s.n_live[1] = run;  // first bin behind the collision class
     }
     run += c[k];
   }

@@ -39,12 +39,16 @@ MODES = {
     "direct": dict(pipeline=0, fast_div=0, tile_shift=9, length_bins=512),
     # the timestep's ~23 driver calls issued one by one instead of recorded into a CUDA graph
     # and submitted as one launch (the default since round 2)
+    # half of the collision class dispatched behind the first 40 % of the streamer CTAs
+    # (whatever the colliders' share of the bank), on a sort without the spatial key
+    "pipeline-stagger": dict(pipeline=1, fast_div=1, tile_shift=-1, length_bins=512,
+                             stagger_at=40, stagger_share=50, stagger_min=0),
     "pipeline-calls": dict(pipeline=1, fast_div=1, tile_shift=8, length_bins=512, step_graph=0),
 }
 
 
 DEFAULTS = dict(MODES["pipeline"], tally_prereduce=0, stage_overlap=1, history_smem_pad=0,
-                step_graph=1)
+                step_graph=1, stagger_at=0, stagger_share=50, stagger_min=35)
 
 
 @pytest.fixture(params=list(MODES))

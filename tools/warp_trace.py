@@ -54,7 +54,14 @@ coll = t[:, 4] > 0
 live = t[:, 5] > 0
 print(f"{args.deck} step {args.step}: kernel {r.kernel_ns / 1e6:.3f} ms, {len(t)} warps recorded, "
       f"{int(coll.sum())} collider warps, {int((~coll & live).sum())} streamer warps")
-for name, m in (("collider", coll), ("streamer", ~coll & live)):
+late = coll & (start > 0.05)  # colliders dispatched behind streamers (option stagger_at)
+groups = [("collider", coll), ("streamer", ~coll & live)]
+if late.any():
+    groups = [("collider@0", coll & ~late), ("collider late", late), ("streamer", ~coll & live)]
+    sm_late = np.bincount(t[late, 2].astype(int), minlength=148)
+    print(f"  late collider warps per SM: min {sm_late.min()} median {int(np.median(sm_late))} "
+          f"max {sm_late.max()} (SMs without any: {int((sm_late == 0).sum())})")
+for name, m in groups:
     if m.any():
         d = end[m] - start[m]
         print(f"  {name:9s} start {start[m].min():.3f}..{start[m].max():.3f} ms  end "
