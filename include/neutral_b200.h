@@ -365,6 +365,10 @@ int nb200_selftest_sincos(const double* x_host, double* sin_host, double* cos_ho
 double nb200_host_sin(double x);
 double nb200_host_cos(double x);
 void nb200_host_sincos(const double* x, long long n, double* sin_out, double* cos_out);
+/* Which 128-slot group of the sorted bank the event loop's CTA `cta` works on under the
+ * stagger_* options (host evaluation of the kernel's own map, history.cu: dispatch_group). */
+unsigned nb200_selftest_dispatch_group(unsigned cta, unsigned n_live, unsigned n_coll,
+                                       int stagger_at, int stagger_share, int stagger_min);
 long long nb200_selftest_host_sincos(const double* x, long long n, double* bad_x);
 
 #ifdef __cplusplus

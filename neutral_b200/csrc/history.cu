@@ -90,8 +90,8 @@ __device__ __forceinline__ unsigned long long trace_now() {
 // sizeable share of the bank but fit the first wave, `stagger_share` percent of their CTAs go
 // out behind the first `stagger_at` percent of the streamer CTAs instead of in front. A
 // permutation of whole groups inside the live prefix; no history changes.
-__device__ __forceinline__ unsigned dispatch_group(const StepArgs& a, unsigned b, unsigned n_live,
-                                                   unsigned n_coll) {
+__host__ __device__ __forceinline__ unsigned dispatch_group(const StepArgs& a, unsigned b,
+                                                            unsigned n_live, unsigned n_coll) {
   if (a.stagger_at <= 0) return b;
   const unsigned T = n_live / kHistoryThreads;   // full groups of the live prefix
   const unsigned NC = n_coll / kHistoryThreads;  // groups of colliders only
@@ -105,6 +105,18 @@ __device__ __forceinline__ unsigned dispatch_group(const StepArgs& a, unsigned b
   if (b < P) return NC + (b - A);       // the first streamers
   if (b < P + nB) return A + (b - P);   // the delayed colliders
   return b;                             // the remaining streamers: NC + (P - A) + (b - P - nB)
+}
+
+// Host-side evaluation of the map (pure integer arithmetic), for tests/test_cabi.py: it has
+// to be a permutation of the groups of the live prefix for any arguments.
+extern "C" unsigned nb200_selftest_dispatch_group(unsigned cta, unsigned n_live, unsigned n_coll,
+                                                  int stagger_at, int stagger_share,
+                                                  int stagger_min) {
+  StepArgs a{};
+  a.stagger_at = stagger_at;
+  a.stagger_share = stagger_share;
+  a.stagger_min = stagger_min;
+  return dispatch_group(a, cta, n_live, n_coll);
 }
 
 template <bool kFastDiv, bool kPreReduce>

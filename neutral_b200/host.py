@@ -50,6 +50,7 @@ EXPORTED_SYMBOLS = [
     "nb200_solve_finish", "nb200_last_step_stats", "nb200_kernel_launches", "nb200_selftest_rng_log",
     "nb200_selftest_log", "nb200_selftest_div", "nb200_selftest_fastmath", "nb200_selftest_cs", "nb200_host_threefry2x64_20",
     "nb200_host_log", "nb200_selftest_sincos", "nb200_host_sin", "nb200_host_cos",
+    "nb200_selftest_dispatch_group",
     "nb200_host_sincos", "nb200_selftest_host_sincos",
     "nb200_bank_capacity", "nb200_bank_gpus", "nb200_bank_append", "nb200_get_option",
     "nb200_bank_set_option", "nb200_bank_solve_finish", "nb200_bank_pending", "nb200_mp_init",

@@ -83,3 +83,40 @@ def test_group_entry_points_refuse_without_a_device(lib):
     rate = C.c_double()
     assert lib.nb200_microbench_red(3, 16 << 20, 10, C.byref(rate)) == -1
     assert b"no CPU fallback" in lib.nb200_last_error()
+
+
+def test_staggered_dispatch_is_a_permutation_of_the_live_groups(lib):
+    """The event loop's CTA -> bank-group map under the stagger_* options (history.cu:
+    dispatch_group, evaluated on the host by the library itself): every group of the live prefix
+    is visited exactly once whatever the arguments, the map is the identity when the option is
+    off, when the colliders are too few or exceed the first wave, and beyond the live prefix;
+    where it applies, the colliders that start with the launch come first and the delayed ones
+    sit behind the requested share of the streamer groups."""
+    import random
+    f = lib.nb200_selftest_dispatch_group
+    f.argtypes = [C.c_uint] * 3 + [C.c_int] * 3
+    f.restype = C.c_uint
+    rng = random.Random(7)
+    cases = [(1_000_000, 55_169, 40, 50, 35), (916_929, 56_606, 55, 35, 40), (1000, 0, 40, 50, 0),
+             (129, 128, 40, 50, 0), (128 * 900, 128 * 889, 40, 50, 0), (5000, 5000, 40, 50, 0)]
+    for _ in range(200):
+        n_live = rng.randrange(0, 300_000)
+        cases.append((n_live, rng.randrange(0, n_live + 1), rng.randrange(0, 96),
+                      rng.randrange(0, 101), rng.randrange(0, 200)))
+    for n_live, n_coll, at, share, mn in cases:
+        groups = (n_live + 127) // 128 + 3  # the grid covers the host's upper bound, not n_live
+        image = [f(b, n_live, n_coll, at, share, mn) for b in range(groups)]
+        assert sorted(image) == list(range(groups)), (n_live, n_coll, at, share, mn)
+        full, nc = n_live // 128, n_coll // 128
+        applies = at > 0 and nc < full and nc <= 148 * 6 and n_coll * 1000 >= mn * n_live
+        if not applies:
+            assert image == list(range(groups))
+            continue
+        assert image[full:] == list(range(full, groups))  # ragged tail and dead groups keep their place
+        delayed = nc * share // 100
+        first = nc - delayed
+        at_group = first + (full - nc) * at // 100
+        assert image[:first] == list(range(first))
+        assert image[at_group:at_group + delayed] == list(range(first, nc))
+    # the csp timestep of profiles/r02/experiments/warp_trace_stagger40_csp_step6.txt
+    assert f(0, 916_929, 56_606, 0, 50, 40) == 0 and f(300, 916_929, 56_606, 40, 50, 40) == 300 + 221
