@@ -1,4 +1,4 @@
-// nb_history.cuh - helpers shared by the event-loop kernels (history.cu, collide.cu).
+// nb_history.cuh - helpers of the event-loop kernel (history.cu).
 #pragma once
 
 #include "nb_device.cuh"
