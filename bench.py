@@ -793,6 +793,13 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
                        "tally_sum": e2e["tally_sum"], "live_particles_out": e2e_live_all,
                        "pipeline": "double-buffered: upload of step i+1 and download of step "
                                    "i-1 overlap the transport of step i"}
+    if e2e:
+        try:  # what the e2e loop downloaded last against the resident run of the same deck
+            line["e2e"]["tally_matches_resident"] = bool(
+                abs(e2e["tally_sum"] - tally_sum) <= 1e-10 * abs(tally_sum))
+            line["e2e"]["live_matches_resident"] = bool(e2e_live_all == int(live.item()))
+        except Exception:  # (no parity pass, no live count): a reported extra, never a gate
+            pass
     stage("other decks")
     if world == 1 and not args.no_decks:
         line["decks"] = time_other_decks(lib, torch, [n for n in OTHER_DECKS if n != deck.name])
